@@ -1,0 +1,135 @@
+// affine.cu — A6: least-squares affine match R ~ s*D + o over the candidates
+// and their mirrors (replaces _process_gpu_batch,
+// /root/reference/fractal.py:757-850, which materialises six (B, 2K, N)
+// temporaries in ~25 generic array kernels).
+//
+// One warp per range, one lane per candidate (32 candidates per pass).  A lane
+// gathers its candidate's domain row (N floats, one or a few 16-byte loads),
+// fits both orientations with fwm::affine_fit — numpy's float32 operation
+// order, so s, o and err are the reference's bits — and the warp takes the
+// first minimum over [plain 0..K-1, mirrored 0..K-1] with a shuffle argmin
+// keyed on (err, position).
+//
+// Bound: HBM (random row gathers): K*N*4 + N*4 + K*4 + 17 bytes per range.
+// The north-star's "precomputed domain sums" are not used: caching sum(D) per
+// domain would save flops this kernel has to spare, while the mirrored sums
+// round differently for N < 8, so they would have to be stored twice.
+#include "common.cuh"
+#include "fwav_math.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Best {
+    float err;
+    int pos;      // orientation * K + candidate slot
+    float s, o;
+    int idx;
+};
+
+__device__ __forceinline__ bool better(float e1, int p1, float e2, int p2) {
+    return e1 < e2 || (e1 == e2 && p1 < p2);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
+              const float *__restrict__ domains, const int32_t *__restrict__ cand, int K, float clipf,
+              int32_t *__restrict__ o_idx, float *__restrict__ o_s, float *__restrict__ o_o,
+              uint8_t *__restrict__ o_sym, float *__restrict__ o_err) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp0; i < n_r; i += n_warps) {
+        const float *rp = ranges + i * N;
+        float rreg[NT > 0 ? NT : 1];
+        if constexpr (NT > 0) {
+#pragma unroll
+            for (int k = 0; k < NT; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(rp + k));
+                rreg[k] = v.x; rreg[k + 1] = v.y; rreg[k + 2] = v.z; rreg[k + 3] = v.w;
+            }
+        }
+        auto r = [&](int k) {
+            if constexpr (NT > 0) return rreg[k];
+            else return __ldg(rp + k);
+        };
+        const float r_mean = fwm::range_mean<NT>(r, N);
+
+        Best best{INFINITY, 0x7fffffff, 0.0f, 0.0f, 0};
+        for (int c0 = 0; c0 < K; c0 += 32) {
+            const int c = c0 + lane;
+            if (c < K) {
+                const int raw = __ldg(cand + i * K + c);
+                const int d = raw < 0 ? 0 : raw;                      // :772-773
+                const float *tp = domains + (long long)d * N;
+                float treg[NT > 0 ? NT : 1];
+                if constexpr (NT > 0) {
+#pragma unroll
+                    for (int k = 0; k < NT; k += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + k));
+                        treg[k] = v.x; treg[k + 1] = v.y; treg[k + 2] = v.z; treg[k + 3] = v.w;
+                    }
+                }
+                auto plain = [&](int k) {
+                    if constexpr (NT > 0) return treg[k];
+                    else return __ldg(tp + k);
+                };
+                auto mirrored = [&](int k) {
+                    if constexpr (NT > 0) return treg[NT - 1 - k];
+                    else return __ldg(tp + (N - 1 - k));
+                };
+                fwm::Fit f0 = fwm::affine_fit<NT>(r, r_mean, plain, N);
+                fwm::Fit f1 = fwm::affine_fit<NT>(r, r_mean, mirrored, N);
+                if (raw < 0) { f0.err = INFINITY; f1.err = INFINITY; }  // :816-817
+                if (better(f0.err, c, best.err, best.pos)) best = Best{f0.err, c, f0.s, f0.o, d};
+                if (better(f1.err, K + c, best.err, best.pos)) best = Best{f1.err, K + c, f1.s, f1.o, d};
+            }
+        }
+        // first argmin over [plain 0..K-1, mirrored 0..K-1]  (:820)
+        float we = best.err;
+        int wp = best.pos;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const float oe = __shfl_xor_sync(kFull, we, off);
+            const int op = __shfl_xor_sync(kFull, wp, off);
+            if (better(oe, op, we, wp)) { we = oe; wp = op; }
+        }
+        if (best.pos == wp) {
+            o_idx[i] = best.idx;
+            o_s[i] = fwm::clip(best.s, -clipf, clipf);                // :823
+            o_o[i] = best.o;                                          // :824
+            o_sym[i] = wp >= K ? 1 : 0;
+            o_err[i] = best.err;
+        }
+    }
+}
+
+}  // namespace
+
+int fwav_launch_affine(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N,
+                       const float *d_domains, int64_t n_d, const int32_t *d_cand, int K,
+                       double s_clip, int32_t *d_idx, float *d_s, float *d_o, uint8_t *d_sym,
+                       float *d_err, cudaStream_t st) {
+    FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
+    FWAV_REQUIRE(ctx, K >= 1, "top_k %d must be positive", K);
+    FWAV_REQUIRE(ctx, n_d >= 1, "affine match needs at least one domain");
+    if (n_r == 0) return FWAV_OK;
+    const float clipf = (float)fabs(s_clip);
+    long long need = (n_r * 32 + 255) / 256;
+    long long cap = (long long)ctx->num_sms * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_ranges) | reinterpret_cast<uintptr_t>(d_domains)) & 15) == 0;
+#define FWAV_AFFINE(NT)                                                                          \
+    affine_kernel<NT><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, d_cand, K, clipf, d_idx, \
+                                            d_s, d_o, d_sym, d_err)
+    if (aligned && N == 4) FWAV_AFFINE(4);
+    else if (aligned && N == 8) FWAV_AFFINE(8);
+    else if (aligned && N == 16) FWAV_AFFINE(16);
+    else if (aligned && N == 32) FWAV_AFFINE(32);
+    else FWAV_AFFINE(0);
+#undef FWAV_AFFINE
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}

@@ -1,0 +1,106 @@
+// common.cuh — context, error plumbing and small device helpers shared by the
+// translation units of libfwav_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fwav_b200.h"
+#include "embed_tables.h"
+
+constexpr int kNumSMsB200 = 148;
+
+struct fwav_ctx {
+    int device = 0;
+    int num_sms = kNumSMsB200;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    int search_impl = FWAV_SEARCH_AUTO;
+    int64_t launches = 0;
+
+    // embedding matrices cached per (N, half)
+    int emb_N = 0, emb_half = 0;
+    double *d_tonal = nullptr, *d_transient = nullptr, *d_w = nullptr;
+
+    // grow-only scratch arenas (device) and a pinned host staging block
+    void *ws[24] = {nullptr};
+    size_t ws_bytes[24] = {0};
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+// scratch slots
+enum {
+    WS_HALF = 0, WS_ACTIVE, WS_CAND, WS_QEMB, WS_DECODE_A, WS_DECODE_RED, WS_UMMA_E, WS_UMMA_Q, WS_UMMA_MISC,
+    // device mirrors of the host-buffer entry points
+    WS_H_SIGNAL, WS_H_RANGES, WS_H_DOMAINS, WS_H_EMB, WS_H_MATCH, WS_H_OUT,
+    WS_COUNT
+};
+static_assert(WS_COUNT <= 24, "grow fwav_ctx::ws");
+
+int fwav_set_error(fwav_ctx *ctx, int code, const char *fmt, ...);
+int fwav_ws_reserve(fwav_ctx *ctx, int slot, size_t bytes, void **out);
+int fwav_embed_tables_device(fwav_ctx *ctx, int N, int half);
+
+#define FWAV_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fwav_set_error((ctx), FWAV_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                                  cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define FWAV_REQUIRE(ctx, cond, ...)                                                           \
+    do {                                                                                       \
+        if (!(cond)) return fwav_set_error((ctx), FWAV_ERR_INVALID, __VA_ARGS__);              \
+    } while (0)
+
+#define FWAV_LAUNCH_CHECK(ctx)                                                                 \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        FWAV_CUDA((ctx), cudaGetLastError());                                                  \
+    } while (0)
+
+static inline cudaStream_t fwav_stream(fwav_ctx *ctx, void *stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+// internal launchers (one per .cu file)
+int fwav_launch_domains(fwav_ctx *ctx, const float *d_signal, int64_t n, int tile, int N, int ds,
+                        float *d_domains, cudaStream_t st);
+int fwav_launch_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int N, int emb_dim,
+                      float *d_emb, cudaStream_t st);
+int fwav_launch_activity(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N, double thr,
+                         int fast_mode, uint8_t *d_active, cudaStream_t st);
+int fwav_launch_topk_ffma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const float *d_emb,
+                          int64_t n_d, int emb_dim, int top_k, const uint8_t *d_active,
+                          int32_t *d_cand, float *d_scores, cudaStream_t st);
+int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const float *d_emb,
+                          int64_t n_d, int emb_dim, int top_k, const uint8_t *d_active,
+                          int32_t *d_cand, float *d_scores, cudaStream_t st);
+bool fwav_topk_umma_supported(int emb_dim, int top_k, int64_t n_q, int64_t n_d);
+int fwav_launch_affine(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N,
+                       const float *d_domains, int64_t n_d, const int32_t *d_cand, int K,
+                       double s_clip, int32_t *d_idx, float *d_s, float *d_o, uint8_t *d_sym,
+                       float *d_err, cudaStream_t st);
+int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
+                       const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
+                       int iterations, double eps, double s_clip, double s_damping, float *d_out,
+                       int *iters_run, float *last_delta, cudaStream_t st);
+
+#if defined(__CUDACC__)
+// streaming loads/stores that do not pollute L1 (data touched once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+#endif

@@ -1,0 +1,208 @@
+// decode.cu — A9: the iterative decoder (replaces the loop of decompress_audio,
+// /root/reference/fractal.py:1411-1467: ten-plus full-size numpy temporaries and
+// two float64 bincounts per iteration).
+//
+// Decoding is range-local (the tiles come from the static domain table,
+// :1414): one thread owns one range for one iteration, reads its current
+// reconstruction (N floats), gathers its tile (N floats), applies
+// fwm::decode_range — numpy's float32 operation order, so the samples are the
+// reference's bits — and writes the next reconstruction.  The overlap
+// "average" of the reference is the identity (every output sample has exactly
+// one contribution, :1406-1408), so it is a plain store; the only cross-range
+// quantity is delta = |next-cur| / |cur|, reduced in a FIXED order: float64
+// per-thread sums -> warp shuffle tree -> per-block partial -> one finalize
+// block that adds the partials in index order.  The convergence test runs on
+// the device; once it fires the remaining iteration launches return at once.
+//
+// Bound: HBM, 12*N + 13 bytes per range per iteration.
+#include "common.cuh"
+#include "fwav_math.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kThreads = 256;
+
+struct DecodeState {
+    int iters_run;
+    int done;
+    float delta;
+    int pad;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads)
+decode_iter_kernel(const float *__restrict__ domains, const int32_t *__restrict__ idx,
+                   const float *__restrict__ s_st, const float *__restrict__ o_st,
+                   const uint8_t *__restrict__ sym, long long n_r, int N, float clipf, int damped,
+                   float one_minus_damp, float damp, int first, const float *__restrict__ cur,
+                   float *__restrict__ nxt, const DecodeState *__restrict__ state,
+                   double *__restrict__ partials) {
+    if (state->done) return;
+    double dsq = 0.0, csq = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_r;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int raw = __ldg(idx + i);
+        const bool dead = raw < 0;                                        // :1399-1426
+        const bool flip = !dead && __ldg(sym + i) != 0;
+        const float sv = dead ? 0.0f : __ldg(s_st + i);
+        const float ov = dead ? 0.0f : __ldg(o_st + i);
+        const float *tp = domains + (long long)(dead ? 0 : raw) * N;
+        const float *cp = cur + i * N;
+        float *np_ = nxt + i * N;
+        if constexpr (NT > 0) {
+            float t[NT], c[NT], w[NT];
+#pragma unroll
+            for (int k = 0; k < NT; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + k));
+                t[k] = v.x; t[k + 1] = v.y; t[k + 2] = v.z; t[k + 3] = v.w;
+            }
+            if (dead) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) t[k] = 0.0f;
+            }
+            if (first) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) c[k] = 0.0f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NT; k += 4) {
+                    const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(cp + k));
+                    c[k] = v.x; c[k + 1] = v.y; c[k + 2] = v.z; c[k + 3] = v.w;
+                }
+            }
+            auto cc = [&](int k) { return c[k]; };
+            auto put = [&](int k, float v) { w[k] = v; };
+            if (flip) {
+                auto tt = [&](int k) { return t[NT - 1 - k]; };
+                fwm::decode_range<NT>(cc, tt, sv, ov, NT, clipf, damped != 0, one_minus_damp, damp, put, &dsq, &csq);
+            } else {
+                auto tt = [&](int k) { return t[k]; };
+                fwm::decode_range<NT>(cc, tt, sv, ov, NT, clipf, damped != 0, one_minus_damp, damp, put, &dsq, &csq);
+            }
+#pragma unroll
+            for (int k = 0; k < NT; k += 4)
+                st_stream_f4(reinterpret_cast<float4 *>(np_ + k), make_float4(w[k], w[k + 1], w[k + 2], w[k + 3]));
+        } else {
+            auto cc = [&](int k) { return first ? 0.0f : cp[k]; };
+            auto tt = [&](int k) { return dead ? 0.0f : __ldg(tp + (flip ? N - 1 - k : k)); };
+            auto put = [&](int k, float v) { np_[k] = v; };
+            fwm::decode_range(cc, tt, sv, ov, N, clipf, damped != 0, one_minus_damp, damp, put, &dsq, &csq);
+        }
+    }
+    // fixed-order block reduction of the two float64 sums
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        dsq += __shfl_down_sync(kFull, dsq, off);
+        csq += __shfl_down_sync(kFull, csq, off);
+    }
+    __shared__ double red[2][kThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = dsq; red[1][warp] = csq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+decode_finalize_kernel(const double *__restrict__ partials, int n_blocks, double eps,
+                       DecodeState *__restrict__ state) {
+    if (state->done) return;
+    // lanes take interleaved partials, then a fixed shuffle tree: same order every run
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += 32) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_down_sync(kFull, a, off);
+        b += __shfl_down_sync(kFull, b, off);
+    }
+    if (threadIdx.x == 0) {
+        const float delta = fwm::decode_delta(a, b);                     // :1460-1461
+        state->delta = delta;
+        state->iters_run += 1;
+        if ((double)delta < eps) state->done = 1;                        // :1465
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+decode_select_kernel(const DecodeState *__restrict__ state, const T *__restrict__ scratch,
+                     T *__restrict__ out, long long n) {
+    if ((state->iters_run & 1) == 0) return;   // result already sits in `out`
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = scratch[i];
+}
+
+}  // namespace
+
+int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
+                       const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
+                       int iterations, double eps, double s_clip, double s_damping, float *d_out,
+                       int *iters_run, float *last_delta, cudaStream_t st) {
+    FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
+    if (iters_run) *iters_run = 0;
+    if (last_delta) *last_delta = 0.0f;
+    if (n_r == 0) return FWAV_OK;
+    FWAV_REQUIRE(ctx, n_d >= 1, "decoder needs at least one domain row");
+    const long long total = (long long)n_r * N;
+    if (iterations <= 0) {   // the reference returns the zero-initialised buffer (:1389)
+        FWAV_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(float) * total, st));
+        FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+        return FWAV_OK;
+    }
+    long long need = (n_r + kThreads - 1) / kThreads;
+    long long cap = (long long)ctx->num_sms * 8;
+    const int grid = (int)(need < cap ? need : cap);
+
+    float *d_scratch = nullptr;
+    double *d_part = nullptr;
+    int rc = fwav_ws_reserve(ctx, WS_DECODE_A, sizeof(float) * (size_t)total, (void **)&d_scratch);
+    if (rc) return rc;
+    rc = fwav_ws_reserve(ctx, WS_DECODE_RED, sizeof(double) * 2 * (size_t)grid + sizeof(DecodeState), (void **)&d_part);
+    if (rc) return rc;
+    DecodeState *d_state = reinterpret_cast<DecodeState *>(d_part + 2 * (size_t)grid);
+    FWAV_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(DecodeState), st));
+
+    const float clipf = (float)fabs(s_clip);
+    const int damped = s_damping > 0 ? 1 : 0;
+    const float omd = (float)(1.0 - s_damping), dmp = (float)s_damping;   // python floats cast to f32 (:1445)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_domains) | reinterpret_cast<uintptr_t>(d_out) |
+                           reinterpret_cast<uintptr_t>(d_scratch)) & 15) == 0;
+    // iteration `it` reads buf[it & 1] and writes buf[(it + 1) & 1]; buf[0] is d_out
+    float *buf[2] = {d_out, d_scratch};
+    for (int it = 0; it < iterations; ++it) {
+        const float *cur = buf[it & 1];
+        float *nxt = buf[(it + 1) & 1];
+#define FWAV_DEC(NT)                                                                               \
+    decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
+                                                      damped, omd, dmp, it == 0, cur, nxt, d_state, d_part)
+        if (aligned && N == 4) FWAV_DEC(4);
+        else if (aligned && N == 8) FWAV_DEC(8);
+        else if (aligned && N == 16) FWAV_DEC(16);
+        else if (aligned && N == 32) FWAV_DEC(32);
+        else FWAV_DEC(0);
+#undef FWAV_DEC
+        FWAV_LAUNCH_CHECK(ctx);
+        decode_finalize_kernel<<<1, 32, 0, st>>>(d_part, grid, eps, d_state);
+        FWAV_LAUNCH_CHECK(ctx);
+    }
+    // an odd iteration count leaves the result in the scratch buffer
+    if (aligned && total % 4 == 0)
+        decode_select_kernel<float4><<<(int)cap, 256, 0, st>>>(
+            d_state, reinterpret_cast<const float4 *>(d_scratch), reinterpret_cast<float4 *>(d_out), total / 4);
+    else
+        decode_select_kernel<float><<<(int)cap, 256, 0, st>>>(d_state, d_scratch, d_out, total);
+    FWAV_LAUNCH_CHECK(ctx);
+    DecodeState h{};
+    FWAV_CUDA(ctx, cudaMemcpyAsync(&h, d_state, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (iters_run) *iters_run = h.iters_run;
+    if (last_delta) *last_delta = h.delta;
+    return FWAV_OK;
+}

@@ -1,0 +1,165 @@
+// embed.cu — A2/A3: the two-head DCT embedding of every domain row (replaces
+// multi_head_embedding driven by build_domain_embeddings,
+// /root/reference/fractal.py:154-208, :238-280 — a serial Python loop at
+// ~24 us/domain in the reference).
+//
+// Both heads are linear maps of the row followed by a norm, so the whole
+// embedding is two small constant matrices (float64, built on the host by
+// embed_tables.h).  For the shapes the reference actually produces
+// (range_size 4/8/16/32 with emb_dim 16) the matrices travel as a
+// __grid_constant__ kernel parameter, so every DFMA reads its coefficient
+// straight from the constant bank; other shapes read them from global memory.
+//
+// HBM traffic per row: 4*N bytes read + 4*emb_dim bytes written (streaming).
+#include "common.cuh"
+#include "fwav_math.cuh"
+
+namespace {
+
+template <int N, int HALF>
+struct TablesP {
+    double tonal[HALF * N];
+    double transient[HALF * N];
+    double w[N];
+};
+
+// Same arithmetic, in the same order, as fwm::embed_row; fully unrolled so the
+// coefficients are constant-bank operands.
+template <int N, int HALF>
+__device__ __forceinline__ void embed_row_static(const float (&x)[N], const TablesP<N, HALF> &T,
+                                                 float (&out)[2 * HALF]) {
+    double ssq = 0.0;
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc = fma((double)x[n], T.tonal[k * N + n], acc);
+        const float v = (float)acc;
+        out[k] = v;
+        ssq += (double)v * (double)v;
+    }
+    const float nrm = npm::sqrt((float)ssq);
+    if (nrm > 1e-8f) {
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) out[k] = npm::div(out[k], nrm);
+    }
+    constexpr int LIVE = HALF < N ? HALF : N;
+    double u[N];
+    u[0] = 0.0 * T.w[0];
+#pragma unroll
+    for (int n = 1; n < N; ++n) u[n] = (double)npm::sub(x[n], x[n - 1]) * T.w[n];
+    double tv[LIVE];
+    double tsq = 0.0;
+#pragma unroll
+    for (int k = 0; k < LIVE; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc = fma(u[n], T.transient[k * N + n], acc);
+        tv[k] = acc;
+        tsq += acc * acc;
+    }
+    const double tn = sqrt(tsq);
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+        float v = 0.0f;
+        if (k < LIVE) v = (float)(tn > 1e-8 ? tv[k] / tn : tv[k]);
+        out[HALF + k] = v;
+    }
+}
+
+template <int N, int HALF>
+__global__ void __launch_bounds__(128)
+embed_static_kernel(const float *__restrict__ rows, long long n_rows, float *__restrict__ emb,
+                    const __grid_constant__ TablesP<N, HALF> T) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        float x[N];
+        const float4 *src = reinterpret_cast<const float4 *>(rows + r * N);
+#pragma unroll
+        for (int k = 0; k < N / 4; ++k) {
+            const float4 q = __ldg(src + k);
+            x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
+        }
+        float out[2 * HALF];
+        embed_row_static<N, HALF>(x, T, out);
+        float4 *dst = reinterpret_cast<float4 *>(emb + r * (2 * HALF));
+#pragma unroll
+        for (int k = 0; k < (2 * HALF) / 4; ++k)
+            dst[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+embed_generic_kernel(const float *__restrict__ rows, long long n_rows, int N, int emb_dim,
+                     const double *__restrict__ tonal, const double *__restrict__ transient,
+                     const double *__restrict__ w, float *__restrict__ emb) {
+    const int half = emb_dim / 2;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        const float *x = rows + r * N;
+        auto row = [&](int i) { return __ldg(x + i); };
+        float *o = emb + r * emb_dim;
+        fwm::embed_row(row, N, half, tonal, transient, w, o);
+        for (int i = 2 * half; i < emb_dim; ++i) o[i] = 0.0f;
+    }
+}
+
+template <int N, int HALF>
+int launch_static(fwav_ctx *ctx, const float *d_rows, int64_t rows, float *d_emb, cudaStream_t st) {
+    const FwavEmbedTables t = fwav_make_embed_tables(N, HALF);
+    TablesP<N, HALF> P;
+    for (int i = 0; i < HALF * N; ++i) { P.tonal[i] = t.tonal[i]; P.transient[i] = t.transient[i]; }
+    for (int i = 0; i < N; ++i) P.w[i] = t.w[i];
+    long long need = (rows + 127) / 128;
+    long long cap = (long long)ctx->num_sms * 8;
+    const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    embed_static_kernel<N, HALF><<<grid, 128, 0, st>>>(d_rows, rows, d_emb, P);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
+}  // namespace
+
+int fwav_embed_tables_device(fwav_ctx *ctx, int N, int half) {
+    if (ctx->emb_N == N && ctx->emb_half == half && ctx->d_tonal) return FWAV_OK;
+    const FwavEmbedTables t = fwav_make_embed_tables(N, half);
+    if (ctx->d_tonal) cudaFree(ctx->d_tonal);
+    if (ctx->d_transient) cudaFree(ctx->d_transient);
+    if (ctx->d_w) cudaFree(ctx->d_w);
+    ctx->d_tonal = ctx->d_transient = ctx->d_w = nullptr;
+    const size_t mb = sizeof(double) * (size_t)half * N;
+    FWAV_CUDA(ctx, cudaMalloc(&ctx->d_tonal, mb));
+    FWAV_CUDA(ctx, cudaMalloc(&ctx->d_transient, mb));
+    FWAV_CUDA(ctx, cudaMalloc(&ctx->d_w, sizeof(double) * N));
+    FWAV_CUDA(ctx, cudaMemcpy(ctx->d_tonal, t.tonal.data(), mb, cudaMemcpyHostToDevice));
+    FWAV_CUDA(ctx, cudaMemcpy(ctx->d_transient, t.transient.data(), mb, cudaMemcpyHostToDevice));
+    FWAV_CUDA(ctx, cudaMemcpy(ctx->d_w, t.w.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+    ctx->emb_N = N;
+    ctx->emb_half = half;
+    return FWAV_OK;
+}
+
+int fwav_launch_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int N, int emb_dim,
+                      float *d_emb, cudaStream_t st) {
+    FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
+    FWAV_REQUIRE(ctx, emb_dim >= 2 && emb_dim <= 256 && emb_dim % 2 == 0,
+                 "emb_dim %d must be even and in [2, 256] (the reference breaks on odd values, "
+                 "fractal.py:275)", emb_dim);
+    if (rows == 0) return FWAV_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_rows) | reinterpret_cast<uintptr_t>(d_emb)) & 15) == 0;
+    if (emb_dim == 16 && aligned) {
+        if (N == 4) return launch_static<4, 8>(ctx, d_rows, rows, d_emb, st);
+        if (N == 8) return launch_static<8, 8>(ctx, d_rows, rows, d_emb, st);
+        if (N == 16) return launch_static<16, 8>(ctx, d_rows, rows, d_emb, st);
+        if (N == 32) return launch_static<32, 8>(ctx, d_rows, rows, d_emb, st);
+    }
+    int rc = fwav_embed_tables_device(ctx, N, emb_dim / 2);
+    if (rc) return rc;
+    long long need = (rows + 127) / 128;
+    long long cap = (long long)ctx->num_sms * 8;
+    const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    embed_generic_kernel<<<grid, 128, 0, st>>>(d_rows, rows, N, emb_dim, ctx->d_tonal, ctx->d_transient,
+                                               ctx->d_w, d_emb);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}

@@ -1,0 +1,279 @@
+"""ctypes binding of libfwav_b200.so (the C ABI in include/fwav_b200.h).
+
+This is the only door between the Python host code and the CUDA kernels.  There
+is NO fallback: if the shared library is missing or no CUDA device is present
+the first call raises FwavError.  The library is loaded lazily so importing the
+package (and forking workers, as the reference's batch mode does,
+fractal.py:1605) never touches CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfwav_b200.so")
+
+SEARCH_AUTO, SEARCH_FFMA, SEARCH_UMMA = 0, 1, 2
+
+c_ctx = C.c_void_p
+c_ptr = C.c_void_p
+i64 = C.c_int64
+
+
+class FwavError(RuntimeError):
+    pass
+
+
+# (name, restype, argtypes) — must list every symbol include/fwav_b200.h declares
+SIGNATURES = [
+    ("fwav_version", C.c_char_p, []),
+    ("fwav_device_count", C.c_int, []),
+    ("fwav_ctx_create", C.c_int, [C.c_int, C.POINTER(c_ctx)]),
+    ("fwav_ctx_destroy", C.c_int, [c_ctx]),
+    ("fwav_last_error", C.c_char_p, [c_ctx]),
+    ("fwav_ctx_sync", C.c_int, [c_ctx]),
+    ("fwav_ctx_set_search_impl", C.c_int, [c_ctx, C.c_int]),
+    ("fwav_ctx_launch_count", i64, [c_ctx]),
+    ("fwav_geometry", C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("fwav_count_domains", i64, [i64, C.c_int, C.c_int]),
+    ("fwav_build_domains", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    ("fwav_embed", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, c_ptr, c_ptr]),
+    ("fwav_topk", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_range_activity", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_double, C.c_int, c_ptr, c_ptr]),
+    ("fwav_affine_match", C.c_int, [c_ctx, c_ptr, i64, C.c_int, c_ptr, i64, c_ptr, C.c_int, C.c_double,
+                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_decode", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int, C.c_int,
+                              C.c_double, C.c_double, C.c_double, c_ptr,
+                              C.POINTER(C.c_int), C.POINTER(C.c_float), c_ptr]),
+    ("fwav_compress_device", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, i64, C.c_int, C.c_int, C.c_int,
+                                       C.c_double, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_compress_host", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                     C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_decode_host", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int, C.c_int,
+                                   C.c_double, C.c_double, C.c_double, c_ptr,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    ("fwav_malloc", C.c_int, [c_ctx, i64, C.POINTER(c_ptr)]),
+    ("fwav_free", C.c_int, [c_ctx, c_ptr]),
+    ("fwav_memcpy_h2d", C.c_int, [c_ctx, c_ptr, c_ptr, i64, c_ptr]),
+    ("fwav_memcpy_d2h", C.c_int, [c_ctx, c_ptr, c_ptr, i64, c_ptr]),
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libfwav_b200.so and type every entry point (no CUDA call yet)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise FwavError(
+                    f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                    "(or make -C audio-compression_b200/csrc). There is no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, res, args in SIGNATURES:
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def geometry(tile_size):
+    lib = load_library()
+    n, d = C.c_int(), C.c_int()
+    lib.fwav_geometry(int(tile_size), C.byref(n), C.byref(d))
+    return n.value, d.value
+
+
+def count_domains(n_samples, tile_size, domain_step):
+    return int(load_library().fwav_count_domains(int(n_samples), int(tile_size), int(domain_step)))
+
+
+def _hp(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class DeviceBuffer:
+    """cudaMalloc'ed block owned through the C ABI; used by the per-kernel
+    entry points when the caller has no tensor library of its own."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = c_ptr()
+        ctx._check(ctx.lib.fwav_malloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, ctx, arr):
+        arr = np.ascontiguousarray(arr)
+        buf = cls(ctx, max(arr.nbytes, 16))
+        if arr.nbytes:
+            ctx._check(ctx.lib.fwav_memcpy_h2d(ctx.h, buf.ptr, _hp(arr), arr.nbytes, None))
+        buf.shape, buf.dtype = arr.shape, arr.dtype
+        return buf
+
+    def to_host(self, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        if out.nbytes:
+            self.ctx._check(self.ctx.lib.fwav_memcpy_d2h(self.ctx.h, _hp(out), self.ptr, out.nbytes, None))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.fwav_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One fwav_ctx: a device, its stream and scratch workspace."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        if self.lib.fwav_device_count() <= 0:
+            raise FwavError("no CUDA device visible: the FWAV hot path runs on B200 only "
+                            "(there is no CPU fallback)")
+        h = c_ctx()
+        rc = self.lib.fwav_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FwavError(f"fwav_ctx_create(device={device}) failed with {rc}")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fwav_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.fwav_last_error(self.h)
+            text = msg.decode("utf-8", "replace") if msg else ""
+            if rc == -1 and text.startswith("mmap length is greater than file size"):
+                raise ValueError(text)      # what np.memmap raises in the reference (fractal.py:1190)
+            raise FwavError(f"fwav error {rc}: {text}")
+
+    # ---- control ----
+    def sync(self):
+        self._check(self.lib.fwav_ctx_sync(self.h))
+
+    def set_search_impl(self, impl):
+        self._check(self.lib.fwav_ctx_set_search_impl(self.h, int(impl)))
+
+    def launch_count(self):
+        return int(self.lib.fwav_ctx_launch_count(self.h))
+
+    def upload(self, arr):
+        return DeviceBuffer.from_host(self, arr)
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    # ---- host-buffer entry points (what fractal.compress_audio / decompress_audio call) ----
+    def compress_host(self, signal, ranges, tile_size, emb_dim, top_k, energy_thresh, fast_mode=True,
+                      query_mode=0, want_domains=True, out=None):
+        signal = _as(signal, np.float32)
+        ranges = _as(ranges, np.float32)
+        n_r = ranges.shape[0]
+        rs, ds = geometry(tile_size)
+        n_d = count_domains(len(signal), tile_size, ds)
+        if out is None:
+            out = dict(
+                domains=np.empty((n_d, rs), np.float32) if want_domains else None,
+                idx=np.empty(n_r, np.int32), s=np.empty(n_r, np.float32), o=np.empty(n_r, np.float32),
+                sym=np.empty(n_r, np.uint8), err=np.empty(n_r, np.float32))
+        self._check(self.lib.fwav_compress_host(
+            self.h, _hp(signal), len(signal), _hp(ranges), n_r, int(tile_size), int(emb_dim), int(top_k),
+            float(energy_thresh), int(bool(fast_mode)), int(query_mode), _hp(out["domains"]),
+            _hp(out["idx"]), _hp(out["s"]), _hp(out["o"]), _hp(out["sym"]), _hp(out["err"])))
+        return out
+
+    def decode_host(self, domains, idx, s, o, sym, range_size, iterations=8, convergence_eps=1e-3,
+                    s_clip=16.0, s_damping=0.0, out=None):
+        domains = _as(domains, np.float32)
+        idx, s, o, sym = _as(idx, np.int32), _as(s, np.float32), _as(o, np.float32), _as(sym, np.uint8)
+        n_r = len(idx)
+        if out is None:
+            out = np.empty(n_r * range_size, np.float32)
+        it, delta = C.c_int(0), C.c_float(0)
+        self._check(self.lib.fwav_decode_host(
+            self.h, _hp(domains), domains.shape[0], _hp(idx), _hp(s), _hp(o), _hp(sym), n_r,
+            int(range_size), int(iterations), float(convergence_eps), float(s_clip), float(s_damping),
+            _hp(out), C.byref(it), C.byref(delta)))
+        return out, it.value, delta.value
+
+    # ---- device-pointer entry points (pointers are ints; stream is an int or None) ----
+    def build_domains(self, d_signal, n, tile_size, range_size, domain_step, d_domains, stream=None):
+        self._check(self.lib.fwav_build_domains(self.h, d_signal, n, tile_size, range_size, domain_step,
+                                                d_domains, stream))
+
+    def embed(self, d_rows, rows, range_size, emb_dim, d_emb, stream=None):
+        self._check(self.lib.fwav_embed(self.h, d_rows, rows, range_size, emb_dim, d_emb, stream))
+
+    def range_activity(self, d_ranges, n_r, range_size, energy_thresh, fast_mode, d_active, stream=None):
+        self._check(self.lib.fwav_range_activity(self.h, d_ranges, n_r, range_size, float(energy_thresh),
+                                                 int(bool(fast_mode)), d_active, stream))
+
+    def topk(self, d_q, n_q, d_emb, n_d, emb_dim, top_k, d_active, d_cand, d_scores=None, stream=None):
+        self._check(self.lib.fwav_topk(self.h, d_q, n_q, d_emb, n_d, emb_dim, top_k, d_active, d_cand,
+                                       d_scores, stream))
+
+    def affine_match(self, d_ranges, n_r, range_size, d_domains, n_d, d_cand, top_k, s_clip,
+                     d_idx, d_s, d_o, d_sym, d_err, stream=None):
+        self._check(self.lib.fwav_affine_match(self.h, d_ranges, n_r, range_size, d_domains, n_d, d_cand,
+                                               top_k, float(s_clip), d_idx, d_s, d_o, d_sym, d_err, stream))
+
+    def decode(self, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size, iterations, convergence_eps,
+               s_clip, s_damping, d_out, stream=None):
+        it, delta = C.c_int(0), C.c_float(0)
+        self._check(self.lib.fwav_decode(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
+                                         int(iterations), float(convergence_eps), float(s_clip),
+                                         float(s_damping), d_out, C.byref(it), C.byref(delta), stream))
+        return it.value, delta.value
+
+    def compress_device(self, d_signal, n, d_ranges, n_r, query_offset, tile_size, emb_dim, top_k,
+                        energy_thresh, fast_mode, query_mode, build, d_domains, d_emb,
+                        d_idx, d_s, d_o, d_sym, d_err, stream=None):
+        self._check(self.lib.fwav_compress_device(
+            self.h, d_signal, n, d_ranges, n_r, query_offset, int(tile_size), int(emb_dim), int(top_k),
+            float(energy_thresh), int(bool(fast_mode)), int(query_mode), int(bool(build)),
+            d_domains, d_emb, d_idx, d_s, d_o, d_sym, d_err, stream))
+
+
+_default = {}
+
+
+def default_context(device=0):
+    """Process-wide context per device, created on first use (fork-safe: the
+    cache is keyed by pid so a forked worker builds its own)."""
+    key = (os.getpid(), int(device))
+    ctx = _default.get(key)
+    if ctx is None:
+        ctx = Context(device)
+        _default[key] = ctx
+    return ctx

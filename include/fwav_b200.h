@@ -1,0 +1,163 @@
+/*
+ * fwav_b200.h — C ABI of the B200-native FWAV hot path (libfwav_b200.so).
+ *
+ * The reference (xavenordu/Audio-Compression, fractal.py) has no FFI layer: its
+ * boundary is the Python function surface.  These entry points are what a
+ * `ctypes` binding inside fractal.py would call in place of the numpy/CuPy
+ * bodies cited beside each declaration (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every call returns 0 on success or a negative fwav_status; the message is
+ *     retrievable with fwav_last_error(ctx).  Nothing throws across the ABI.
+ *   - `d_` parameters are DEVICE pointers on the context's device, `h_`
+ *     parameters are HOST pointers.  The caller owns every data buffer; the
+ *     context owns its stream and scratch workspace.
+ *   - `stream` is a cudaStream_t passed as void*; NULL means the context's own
+ *     stream.  Device-pointer calls are asynchronous on that stream unless
+ *     stated otherwise; host-pointer calls return after the results are in the
+ *     host buffers.
+ *   - one context per host thread; contexts are created lazily by callers so a
+ *     forked worker can initialise CUDA itself (fractal.py:1605 runs files in a
+ *     multiprocessing.Pool).
+ *   - all floating point data is IEEE binary32, row-major.
+ */
+#ifndef FWAV_B200_H
+#define FWAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fwav_ctx fwav_ctx;
+
+typedef enum fwav_status {
+    FWAV_OK = 0,
+    FWAV_ERR_INVALID = -1,     /* bad argument (message says which) */
+    FWAV_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    FWAV_ERR_UNSUPPORTED = -3, /* geometry outside the compiled kernels */
+    FWAV_ERR_NOMEM = -4
+} fwav_status;
+
+/* Which kernel computes the similarity + top-K contraction. */
+typedef enum fwav_search_impl {
+    FWAV_SEARCH_AUTO = 0,  /* tensor-core path when the shape allows it */
+    FWAV_SEARCH_FFMA = 1,  /* FP32 FFMA warp-select kernel */
+    FWAV_SEARCH_UMMA = 2   /* tcgen05 3xTF32 kernel + exact FP32 re-score */
+} fwav_search_impl;
+
+const char *fwav_version(void);
+int fwav_device_count(void);
+
+int fwav_ctx_create(int device, fwav_ctx **out);
+int fwav_ctx_destroy(fwav_ctx *ctx);
+const char *fwav_last_error(const fwav_ctx *ctx);
+/* Block until everything queued on the context's stream has finished. */
+int fwav_ctx_sync(fwav_ctx *ctx);
+/* Select the search kernel for subsequent calls (default FWAV_SEARCH_AUTO). */
+int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl);
+/* Number of kernels this library has launched through `ctx` since creation. */
+int64_t fwav_ctx_launch_count(const fwav_ctx *ctx);
+
+/* Derived geometry of compress_audio (fractal.py:1070-1071) and the domain
+ * count of build_domains_memmap (fractal.py:297-304). */
+int fwav_geometry(int tile_size, int *range_size, int *domain_step);
+int64_t fwav_count_domains(int64_t n_samples, int tile_size, int domain_step);
+
+/* A1 — replaces build_domains_memmap (fractal.py:285-334).
+ * d_domains[j*range_size + k] = numpy-order float32 mean of the k-th run of
+ * tile_size/range_size samples of the window starting at j*domain_step.
+ * Bit-identical to the reference's memmap contents. */
+int fwav_build_domains(fwav_ctx *ctx, const float *d_signal, int64_t n_samples,
+                       int tile_size, int range_size, int domain_step,
+                       float *d_domains, void *stream);
+
+/* A2/A3 — replaces multi_head_embedding over every row
+ * (fractal.py:154-208 called from build_domain_embeddings :271-277).
+ * d_emb is (rows, emb_dim): [tonal emb_dim/2 | transient | zero pad]. */
+int fwav_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int range_size,
+               int emb_dim, float *d_emb, void *stream);
+
+/* A4/A5 — replaces cpu_worker's linear search + pad_candidates
+ * (fractal.py:535-552, 598-623) for all queries at once.
+ * d_cand is (n_queries, top_k) int32: indices of the top_k largest
+ * d_emb·q, best first, -1 padded.  d_active (may be NULL) marks queries to
+ * search; rows of inactive queries are filled with -1 (energy prune, :602).
+ * d_scores (may be NULL) receives the matching scores. */
+int fwav_topk(fwav_ctx *ctx, const float *d_queries, int64_t n_queries,
+              const float *d_emb, int64_t n_domains, int emb_dim, int top_k,
+              const uint8_t *d_active, int32_t *d_cand, float *d_scores, void *stream);
+
+/* Energy prune flags of cpu_worker (fractal.py:602):
+ * d_active[i] = !(fast_mode && mean(range_i^2) < 0.75*energy_thresh). */
+int fwav_range_activity(fwav_ctx *ctx, const float *d_ranges, int64_t n_ranges,
+                        int range_size, double energy_thresh, int fast_mode,
+                        uint8_t *d_active, void *stream);
+
+/* A6 — replaces _process_gpu_batch (fractal.py:757-850): least-squares
+ * R ~ s*D + o over the candidates and their mirrors, first argmin of the L2
+ * residual, s clipped to +-s_clip afterwards.  Arithmetic follows numpy's
+ * float32 operation order, so results are bit-identical given the same
+ * candidate table. */
+int fwav_affine_match(fwav_ctx *ctx, const float *d_ranges, int64_t n_ranges, int range_size,
+                      const float *d_domains, int64_t n_domains,
+                      const int32_t *d_cand, int top_k, double s_clip,
+                      int32_t *d_idx, float *d_s, float *d_o, uint8_t *d_sym, float *d_err,
+                      void *stream);
+
+/* A9 — replaces the iteration loop of decompress_audio (fractal.py:1411-1467).
+ * d_out must hold n_ranges*range_size floats.  The convergence test runs on
+ * the device; *iters_run and *last_delta are written after an internal sync. */
+int fwav_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
+                const int32_t *d_idx, const float *d_s, const float *d_o, const uint8_t *d_sym,
+                int64_t n_ranges, int range_size, int iterations, double convergence_eps,
+                double s_clip, double s_damping, float *d_out,
+                int *iters_run, float *last_delta, void *stream);
+
+/* Device pipeline A1..A7 on resident inputs: replaces the process/queue
+ * pipeline of compress_audio (fractal.py:1114-1245) between "ranges framed"
+ * and "matches collected".  d_signal is the raw signal (domains are built
+ * from it, :1120), d_ranges the masked, reflect-padded, framed ranges (:1112).
+ * Queries are rows [query_offset, query_offset+n_ranges) of the domain
+ * embedding table when query_mode==0 (the reference's live aliasing,
+ * :1190-1195) or embeddings of the ranges themselves when query_mode==1.
+ * d_domains (n_domains*range_size) and d_emb (n_domains*emb_dim) are outputs
+ * the caller keeps; pass build=0 to reuse tables already built there. */
+int fwav_compress_device(fwav_ctx *ctx, const float *d_signal, int64_t n_samples,
+                         const float *d_ranges, int64_t n_ranges, int64_t query_offset,
+                         int tile_size, int emb_dim, int top_k, double energy_thresh,
+                         int fast_mode, int query_mode, int build,
+                         float *d_domains, float *d_emb,
+                         int32_t *d_idx, float *d_s, float *d_o, uint8_t *d_sym, float *d_err,
+                         void *stream);
+
+/* Host-buffer form of the same pipeline (what compress_audio calls):
+ * copies the signal and ranges in, runs the pipeline, copies domains and
+ * matches out.  h_domains may be NULL when the caller does not want them. */
+int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples,
+                       const float *h_ranges, int64_t n_ranges,
+                       int tile_size, int emb_dim, int top_k, double energy_thresh,
+                       int fast_mode, int query_mode,
+                       float *h_domains,
+                       int32_t *h_idx, float *h_s, float *h_o, uint8_t *h_sym, float *h_err);
+
+/* Host-buffer decoder (what decompress_audio calls). h_out: n_ranges*range_size. */
+int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains,
+                     const int32_t *h_idx, const float *h_s, const float *h_o, const uint8_t *h_sym,
+                     int64_t n_ranges, int range_size, int iterations, double convergence_eps,
+                     double s_clip, double s_damping, float *h_out,
+                     int *iters_run, float *last_delta);
+
+/* Plain device memory helpers so a host language without a CUDA binding can
+ * drive the device-pointer entry points. */
+int fwav_malloc(fwav_ctx *ctx, int64_t bytes, void **d_ptr);
+int fwav_free(fwav_ctx *ctx, void *d_ptr);
+int fwav_memcpy_h2d(fwav_ctx *ctx, void *d_dst, const void *h_src, int64_t bytes, void *stream);
+int fwav_memcpy_d2h(fwav_ctx *ctx, void *h_dst, const void *d_src, int64_t bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWAV_B200_H */

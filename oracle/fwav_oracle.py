@@ -135,7 +135,7 @@ def build_domains(signal, tile_size, range_size, domain_step, block=500):
 # ----------------------------------------------------------------------------
 # A2/A3  embeddings                                  fractal.py:154-208, 238-280
 # ----------------------------------------------------------------------------
-def tonal_head(rows, k):
+def tonal_head(rows, k, fast_norm=False):
     """`tile_embedding`: f32 orthonormal DCT-II, x linspace(1,2,N) in f64, drop
     DC, keep k, zero-pad to k, f32 L2-normalise when norm > 1e-8 (fractal.py:178-208)."""
     rows = np.asarray(rows, dtype=np.float32)
@@ -145,6 +145,11 @@ def tonal_head(rows, k):
     take = min(k, max(0, n - 1))                                    # :192-193
     head = np.zeros((n_rows, k), dtype=np.float32)
     head[:, :take] = spec[:, 1:1 + take].astype(np.float32)         # :195
+    if fast_norm:       # bulk tables for the CPU baseline leg: same math, may differ in the last bit
+        nrm = np.sqrt(np.sum(head * head, axis=1, dtype=np.float32))
+        ok = nrm > 1e-8
+        head[ok] = head[ok] / nrm[ok, None]
+        return head
     for i in range(n_rows):                                         # :205-207, per-row f32 norm
         nrm = np.linalg.norm(head[i])
         if nrm > 1e-8:
@@ -152,7 +157,7 @@ def tonal_head(rows, k):
     return head
 
 
-def transient_head(rows, k):
+def transient_head(rows, k, fast_norm=False):
     """`transient_embedding`: first difference (prepend x0), x linspace(1,2,N),
     f64 orthonormal DCT-II, keep the first min(k,N) INCLUDING DC, normalise in
     f64 when norm > 1e-8, cast to f32 (fractal.py:154-164)."""
@@ -161,6 +166,12 @@ def transient_head(rows, k):
     diff = np.diff(rows, axis=1, prepend=rows[:, :1])               # :156 (f32)
     diff = diff * np.linspace(1.0, 2.0, n)                          # :158 (-> f64)
     spec = _dct(diff, axis=1, norm="ortho")[:, :k]                  # :159-160
+    if fast_norm:
+        nrm = np.sqrt(np.sum(spec * spec, axis=1))
+        ok = nrm > 1e-8
+        spec = spec.copy()
+        spec[ok] = spec[ok] / nrm[ok, None]
+        return spec.astype(np.float32)
     out = np.empty(spec.shape, dtype=np.float32)
     for i in range(n_rows):                                         # :161-164
         v = spec[i]
@@ -171,13 +182,13 @@ def transient_head(rows, k):
     return out
 
 
-def embed_rows(rows, emb_dim=16):
+def embed_rows(rows, emb_dim=16, fast_norm=False):
     """`multi_head_embedding(tile, emb_dim//2, emb_dim//2)` for every row
     (fractal.py:166-175 called from :271-277): [tonal | transient | zero pad]."""
     half = emb_dim // 2
     rows = np.asarray(rows, dtype=np.float32)
-    ton = tonal_head(rows, half)
-    tra = transient_head(rows, half)
+    ton = tonal_head(rows, half, fast_norm)
+    tra = transient_head(rows, half, fast_norm)
     out = np.zeros((rows.shape[0], emb_dim), dtype=np.float32)
     out[:, :half] = ton
     out[:, half:half + tra.shape[1]] = tra                          # :170-174 pad at the END

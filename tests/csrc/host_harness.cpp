@@ -1,0 +1,139 @@
+// host_harness.cpp — TEST INFRASTRUCTURE.  Compiles the host/device math of
+// audio-compression_b200/csrc (np_math.cuh, fwav_math.cuh, embed_tables.h) for
+// the CPU so tests/test_host_math.py can pin it to the reference's golden
+// vectors without a GPU.  It is never linked into libfwav_b200.so and the
+// product never loads it.
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "fwav_math.cuh"
+#include "embed_tables.h"
+
+template <int NS, class R, class T>
+static fwm::Fit fit_dispatch(R r, float r_mean, T t, int N) {
+    return fwm::affine_fit<NS>(r, r_mean, t, N);
+}
+#define HH_BY_N(N, CALL)                        \
+    ((N) == 4 ? CALL(4) : (N) == 8 ? CALL(8) : (N) == 16 ? CALL(16) : (N) == 32 ? CALL(32) : CALL(0))
+
+extern "C" {
+
+float hh_np_mean(const float *a, int n) {
+    auto at = [&](int i) { return a[i]; };
+    return npm::np_mean<3>(at, n);
+}
+
+// same decomposition as domains.cu: half sums when run == 256, generic otherwise
+void hh_build_domains(const float *sig, long long n, int tile, int N, int ds, float *out, int force_generic) {
+    long long nd = n < tile ? 0 : (n - tile) / ds + 1;
+    int run = tile / N;
+    auto s = [&](long long i) { return sig[i]; };
+    for (long long j = 0; j < nd; ++j)
+        for (int k = 0; k < N; ++k) {
+            long long start = j * ds + (long long)k * run;
+            if (run == 256 && !force_generic)
+                out[j * N + k] = fwm::domain_from_halves(fwm::half_sum128(s, start), fwm::half_sum128(s, start + 128));
+            else
+                out[j * N + k] = fwm::domain_value(s, start, run);
+        }
+}
+
+void hh_embed(const float *rows, long long n_rows, int N, int emb_dim, float *out) {
+    int half = emb_dim / 2;
+    FwavEmbedTables t = fwav_make_embed_tables(N, half);
+    std::vector<float> tmp(2 * half);
+    for (long long r = 0; r < n_rows; ++r) {
+        const float *x = rows + r * N;
+        auto row = [&](int i) { return x[i]; };
+        fwm::embed_row(row, N, half, t.tonal.data(), t.transient.data(), t.w.data(), tmp.data());
+        float *o = out + r * emb_dim;
+        for (int i = 0; i < emb_dim; ++i) o[i] = i < 2 * half ? tmp[i] : 0.0f;
+    }
+}
+
+void hh_activity(const float *ranges, long long n_r, int N, double thr, int fast, uint8_t *act) {
+    for (long long i = 0; i < n_r; ++i) {
+        const float *r = ranges + i * N;
+        auto row = [&](int k) { return r[k]; };
+        bool p;
+        if (N == 4) p = fwm::range_is_pruned<4>(row, N, thr, fast);          // same static paths as the kernels
+        else if (N == 16) p = fwm::range_is_pruned<16>(row, N, thr, fast);
+        else p = fwm::range_is_pruned(row, N, thr, fast);
+        act[i] = p ? 0 : 1;
+    }
+}
+
+void hh_affine(const float *ranges, long long n_r, int N, const float *domains, const int32_t *cand, int K,
+               double s_clip, int32_t *idx, float *s, float *o, uint8_t *sym, float *err) {
+    const float clipf = (float)std::fabs(s_clip);
+    for (long long i = 0; i < n_r; ++i) {
+        const float *r = ranges + i * N;
+        auto rr = [&](int k) { return r[k]; };
+#define HH_MEAN(NS) fwm::range_mean<NS>(rr, N)
+        const float r_mean = HH_BY_N(N, HH_MEAN);
+        float best = std::numeric_limits<float>::infinity();
+        int best_pos = -1;
+        fwm::Fit best_fit{0, 0, 0};
+        for (int orient = 0; orient < 2; ++orient)
+            for (int c = 0; c < K; ++c) {
+                int raw = cand[i * K + c];
+                int d = raw < 0 ? 0 : raw;
+                const float *t = domains + (long long)d * N;
+                fwm::Fit f;
+#define HH_FIT(NS) fit_dispatch<NS>(rr, r_mean, tt, N)
+                if (orient == 0) { auto tt = [&](int k) { return t[k]; }; f = HH_BY_N(N, HH_FIT); }
+                else { auto tt = [&](int k) { return t[N - 1 - k]; }; f = HH_BY_N(N, HH_FIT); }
+                if (raw < 0) f.err = std::numeric_limits<float>::infinity();
+                int pos = orient * K + c;
+                if (best_pos < 0 || f.err < best) { best = f.err; best_pos = pos; best_fit = f; }
+            }
+        int c = best_pos % K;
+        int raw = cand[i * K + c];
+        idx[i] = raw < 0 ? 0 : raw;
+        s[i] = fwm::clip(best_fit.s, -clipf, clipf);
+        o[i] = best_fit.o;
+        sym[i] = best_pos >= K;
+        err[i] = best_fit.err;
+    }
+}
+
+// full decoder loop on the CPU with the device's per-range function
+int hh_decode(const float *domains, const int32_t *idx, const float *s, const float *o, const uint8_t *sym,
+              long long n_r, int N, int iterations, double eps, double s_clip, double s_damping,
+              float *out, float *last_delta) {
+    std::vector<float> a((size_t)n_r * N, 0.0f), b((size_t)n_r * N, 0.0f);
+    float *cur = a.data(), *nxt = b.data();
+    const float clipf = (float)std::fabs(s_clip);
+    const bool damped = s_damping > 0;
+    const float omd = (float)(1.0 - s_damping), dmp = (float)s_damping;
+    int it = 0;
+    float delta = 0;
+    for (; it < iterations;) {
+        double dsq = 0, csq = 0;
+        for (long long i = 0; i < n_r; ++i) {
+            const bool dead = idx[i] < 0;
+            const float *t = domains + (long long)(dead ? 0 : idx[i]) * N;
+            const bool flip = !dead && sym[i];
+            const float *c = cur + i * N;
+            float *w = nxt + i * N;
+            auto cc = [&](int k) { return c[k]; };
+            auto tt = [&](int k) { return dead ? 0.0f : (flip ? t[N - 1 - k] : t[k]); };
+            auto put = [&](int k, float v) { w[k] = v; };
+#define HH_DEC(NS) (fwm::decode_range<NS>(cc, tt, dead ? 0.0f : s[i], dead ? 0.0f : o[i], N, clipf, damped, omd, dmp, put, &dsq, &csq), 0)
+            (void)HH_BY_N(N, HH_DEC);
+        }
+        delta = fwm::decode_delta(dsq, csq);
+        float *tmp = cur; cur = nxt; nxt = tmp;
+        ++it;
+        if ((double)delta < eps) break;
+    }
+    std::memcpy(out, cur, sizeof(float) * (size_t)n_r * N);
+    *last_delta = delta;
+    return it;
+}
+
+float hh_score(const float *q, const float *e, int dim) { return fwm::score_chain(q, e, dim); }
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+"""The kernels' per-element math (np_math.cuh / fwav_math.cuh), compiled for the
+CPU, against numpy and the reference-generated golden vectors.  This is what
+makes the GPU results predictable before a GPU is touched."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from host_harness import Harness
+
+H = Harness()
+ALL = ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024",
+       "music_k64", "tiny_kfull", "sine_t1100", "music_t3000"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_pairwise_mean_matches_numpy():
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 40)) + [63, 64, 100, 127, 128, 129, 136, 255, 256, 257, 272, 275, 300, 511]:
+        for _ in range(5):
+            a = (rng.standard_normal(n) * 10 ** rng.uniform(-3, 4)).astype(np.float32)
+            want = a.reshape(1, n).mean(axis=1, dtype=np.float32)[0]
+            assert H.np_mean(a).view(np.uint32) == want.view(np.uint32), n
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_domains_bit_exact(name):
+    g = golden(name)
+    tile, N, ds = int(g["tile_size"]), int(g["range_size"]), int(g["domain_step"])
+    got = H.build_domains(g["signal"], tile, N, ds)
+    assert np.array_equal(bits(got), bits(g["domains"]))
+    if tile // N == 256:
+        assert np.array_equal(bits(H.build_domains(g["signal"], tile, N, ds, force_generic=True)), bits(g["domains"]))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_embedding_close(name):
+    g = golden(name)
+    got = H.embed(g["domains"], int(g["emb_dim"]))
+    assert np.abs(got - g["embeddings"]).max() <= 2e-6
+    # padding layout: [tonal | transient | zeros]
+    assert np.array_equal(got == 0, g["embeddings"] == 0) or int(g["range_size"]) >= 9
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_affine_bit_exact_given_candidates(name):
+    g = golden(name)
+    got = H.affine(g["ranges"], g["domains"], g["candidates"])
+    assert np.array_equal(got["idx"], g["idx"])
+    assert np.array_equal(got["sym"], g["sym"])
+    for k in ("s", "o", "err"):
+        assert np.array_equal(bits(got[k]), bits(g[k])), k
+    act = H.activity(g["ranges"], float(g["energy_thresh"]))
+    assert np.array_equal(act == 0, (g["candidates"] < 0).all(axis=1))
+
+
+@pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024",
+                                  "float_t1024", "sentinel_decode", "music_t3000"])
+def test_decode_bit_exact(name):
+    g = golden(name)
+    N = int(g["range_size"])
+    variants = {
+        "default": dict(iterations=8, eps=1e-3),
+        "damp50": dict(iterations=8, eps=0.0, s_damping=0.5),
+        "damp25_clip2": dict(iterations=5, eps=1e-3, s_damping=0.25, s_clip=2.0),
+    }
+    for tag, kw in variants.items():
+        if "dec_" + tag not in g:
+            continue
+        out, it, delta = H.decode(g["domains"], g["idx"], g["s"], g["o"], g["sym"], N, **kw)
+        want = g["dec_" + tag]
+        assert np.array_equal(bits(out[:len(want)]), bits(want)), tag
