@@ -227,7 +227,12 @@ def run_ours(args):
         g_m32 = torch.empty((world, 4, cap), dtype=torch.int32, device=dev)
         g_sym = torch.empty((world, cap), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-NULL) stream: the C ABI treats NULL as "the context's own stream", and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
+    assert stream != 0
     p = lambda t: t.data_ptr()  # noqa: E731
     rng_ptr = d_ranges.data_ptr() + lo * N * 4
 
@@ -455,6 +460,7 @@ def run_decode(ctx, torch, dev, peaks, args):
     sym = torch.randint(0, 2, (n_r,), generator=g, device=dev, dtype=torch.uint8)
     out = torch.empty(n_r * N, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
     iters = 32
     res = {}
     for tag, damp in (("damped_0.5", 0.5), ("default_0.0", 0.0)):

@@ -41,11 +41,6 @@ def set_impl(ctx, impl):
     ctx.set_search_impl({"ffma": _lib.SEARCH_FFMA, "umma": _lib.SEARCH_UMMA, "auto": _lib.SEARCH_AUTO}[impl])
 
 
-def umma_covers(ctx, emb_dim, k):
-    """Ask the library (AUTO resolves to the tensor path only when it is built for the shape)."""
-    return getattr(ctx, "_umma_probe", None) is not False
-
-
 # ------------------------------------------------------------------ per-kernel
 @pytest.mark.parametrize("name", ALL)
 def test_domains_bit_exact(ctx, name):
@@ -84,9 +79,26 @@ def test_embedding_generic_shapes(ctx):
         assert np.abs(got - want).max() <= 2e-6, (N, ed)
 
 
+def boundary_gap(queries, embs, k):
+    """Oracle-side ambiguity of each query's K boundary: score[K-th] - score[(K+1)-th].
+    When it is at rounding level the reference's own candidate set depends on the
+    BLAS kernel's accumulation order and on argpartition's tie handling."""
+    gaps = np.full(len(queries), np.inf, dtype=np.float64)
+    if len(embs) <= k:
+        return gaps
+    for i, q in enumerate(queries):
+        top = np.partition(embs @ q, -(k + 1))[-(k + 1):]
+        top.sort()
+        gaps[i] = float(top[1]) - float(top[0])
+    return gaps
+
+
 def check_candidates(got, want, queries, embs, k, active):
-    """Sets must agree; any difference has to sit on a rounding-level K boundary."""
-    n_bad = 0
+    """Candidate sets must be identical wherever the oracle's K boundary is
+    unambiguous; elsewhere every difference has to sit on that boundary."""
+    gaps = boundary_gap(queries, embs, k)
+    ambiguous = gaps <= SCORE_TOL
+    n_diff = 0
     for i in range(len(want)):
         if not active[i]:
             assert (got[i] == -1).all()
@@ -95,12 +107,13 @@ def check_candidates(got, want, queries, embs, k, active):
         assert len(gs) == len(ws) == min(k, len(embs))
         if gs == ws:
             continue
-        n_bad += 1
+        assert ambiguous[i], (i, gaps[i], sorted(gs ^ ws))
+        n_diff += 1
         sc = embs @ queries[i]
         kth = np.sort(sc)[-k]
         for j in gs ^ ws:
             assert abs(sc[j] - kth) <= SCORE_TOL, (i, j, sc[j], kth)
-    return n_bad
+    return n_diff, int(ambiguous[active].sum())
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -125,8 +138,9 @@ def test_topk_candidates(ctx, name, impl):
     set_impl(ctx, "auto")
     got = d_cand.to_host((n_r, k), np.int32)
     sc = d_sc.to_host((n_r, k), np.float32)
-    bad = check_candidates(got, g["candidates"], embs[:n_r], embs, k, active)
-    assert bad <= max(1, n_r // 200), bad
+    n_diff, n_amb = check_candidates(got, g["candidates"], embs[:n_r], embs, k, active)
+    print(f"{name}/{impl}: {n_diff} candidate sets differ, all among the {n_amb} of {n_r} ranges whose "
+          f"K boundary is tied within {SCORE_TOL:g} in the oracle's own scores")
     # rows are best-first with the canonical float32 score and ties broken by index
     live = got >= 0
     for i in np.flatnonzero(active)[:200]:
@@ -216,8 +230,10 @@ def classify_matches(res, g, top_k):
     """Every (idx, sym) difference must be excused by a rule the north star states."""
     want = O.affine_match(g["ranges"], g["candidates"], g["domains"], want_all=True)
     diff = np.flatnonzero((res["idx"] != g["idx"]) | (res["sym"] != g["sym"]))
-    stats = dict(total=len(g["idx"]), differ=len(diff), near_tie=0, alias=0, boundary=0)
     embs, doms = g["embeddings"], g["domains"]
+    gaps = boundary_gap(embs[:len(g["idx"])], embs, top_k)
+    stats = dict(total=len(g["idx"]), differ=len(diff), near_tie=0, alias=0, boundary=0,
+                 ambiguous=int((gaps <= SCORE_TOL).sum()))
     for i in diff:
         e = np.sort(want["all_err"][i])
         if np.isfinite(e[1]) and abs(e[1] - e[0]) <= 1e-6 * max(abs(e[0]), 1e-30):
@@ -227,6 +243,7 @@ def classify_matches(res, g, top_k):
             stats["alias"] += 1            # bit-identical domain rows: same s, o, err
             assert bits(res["s"][i:i + 1])[0] == bits(g["s"][i:i + 1])[0]
             continue
+        assert gaps[i] <= SCORE_TOL, (i, gaps[i])     # only a tied K boundary may change the winner
         sc = embs @ embs[i]
         kth = np.sort(sc)[-top_k]
         j = res["idx"][i]
@@ -259,7 +276,7 @@ def test_compress_end_to_end(ctx, name, impl):
     set_impl(ctx, "auto")
     assert np.array_equal(bits(res["domains"]), bits(g["domains"]))
     st = classify_matches(res, g, int(g["top_k"]))
-    assert st["boundary"] <= max(1, st["total"] // 200), st
+    assert st["boundary"] <= st["ambiguous"], st
     print(name, impl, st)
 
 
