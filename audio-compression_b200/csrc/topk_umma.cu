@@ -22,10 +22,11 @@
 //     chunk to its maximum with 3-input max instructions and compare it with the
 //     row's running threshold; only chunks that beat it take the warp-cooperative
 //     insertion path into the row's candidate list in shared memory;
-//   * a row keeps its 48 best candidates (top_k <= 32 plus a 16-entry margin) and
-//     16 pending ones; the thread that owns the row appends with one 8-byte store
-//     and the warp merges a row only when its pending area is full, so the
-//     threshold moves once per 16 candidates; at the end every kept candidate is
+//   * a row keeps its 48 best candidates (top_k <= 32 plus a 16-entry margin) as
+//     sorted 64-bit keys; an insertion is one ballot for the position and a
+//     one-slot shift, and the accumulator buffer is handed back to the MMA warp
+//     BEFORE a stage is examined, so a warp in the rare path does not stall the
+//     tensor pipe; at the end every kept candidate is
 //     re-scored with the canonical float32 FMA chain and the best top_k are written
 //     best-first, so the result equals the FFMA kernel's unless more than 16
 //     domains tie with the K-th score at the 3xTF32 rounding level (~1e-6).
@@ -47,8 +48,7 @@ constexpr int kStages = 3;
 constexpr int kThreads = 320;          // 8 epilogue warps + producer/alloc warp + MMA warp
 constexpr int kChunks = kDTile / 32;   // 32-column TMEM chunks per stage
 constexpr int kKeep = 48;              // candidates kept per query (top_k <= 32 plus a 16-entry margin)
-constexpr int kPend = 16;              // pending (not yet merged) candidates per query
-constexpr int kCap = kKeep + kPend;    // 64 eight-byte entries per query
+constexpr int kCap = kKeep;            // eight-byte keys per query row in shared memory
 constexpr uint32_t kPartBytes = kDTile * ED * 4;       // 8 KB: one 128-row hi or lo tile
 constexpr uint32_t kTileBytes = 2 * kPartBytes;        // 16 KB: hi | lo
 constexpr uint32_t kABytes = 2 * kTileBytes;           // 32 KB: two query halves
@@ -180,11 +180,8 @@ pack_tf32_tiles_kernel(const float *__restrict__ src, long long n_rows, long lon
 // Candidate bookkeeping.  A candidate is one 64-bit key
 //     [ order-preserving bits of the score | 0xFFFFFFFF - domain index ]
 // so "ranks before" (score descending, index ascending) is a plain unsigned
-// compare.  Every query row owns kCap keys in shared memory: slots [0, kKeep) are
-// the current best list, slots [kKeep, kCap) collect candidates that beat the
-// row's threshold since the last merge.  Appending is a single 8-byte store by
-// the thread that owns the row; the threshold only moves at merges, which are
-// warp-cooperative and happen once per kPend appended candidates.
+// compare.  Every query row owns kKeep keys in shared memory, kept sorted
+// best-first; the row's threshold is the score of the last one.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t order_bits(float s) {
     const uint32_t u = __float_as_uint(s);
@@ -201,22 +198,17 @@ __device__ __forceinline__ unsigned long long make_key(float s, int id) {
     return ((unsigned long long)order_bits(s) << 32) | (0xFFFFFFFFu - (uint32_t)id);
 }
 
-// Merge one row: keep the kKeep best of its kKeep + cnt keys, sorted best-first in
-// slots [0, kKeep).  Returns the new threshold (score of the kKeep-th best, -inf
-// while the list is not full).  All 32 lanes take part.
-__device__ __noinline__ float merge_row(unsigned long long *keys, int cnt, int lane) {
-    const int n = kKeep + cnt;
+// Warp-cooperative sorted insertion of x (known to beat the row's last key): a
+// ballot gives its position, every lane moves its two keys one slot down, the
+// last key falls off.  ~25 instructions, no loops.  Returns the new threshold.
+__device__ __forceinline__ float insert_sorted(unsigned long long *keys, unsigned long long x, int lane) {
+    const bool has1 = lane + 32 < kKeep;
     const unsigned long long k0 = keys[lane];
-    const unsigned long long k1 = (lane + 32 < n) ? keys[lane + 32] : 0ull;   // 0 ranks after everything
-    int r0 = 0, r1 = 0;
-    for (int o = 0; o < n; ++o) {
-        const unsigned long long ko = keys[o];       // broadcast read
-        r0 += ko > k0 ? 1 : 0;
-        r1 += ko > k1 ? 1 : 0;
-    }
-    __syncwarp();
-    if (r0 < kKeep) keys[r0] = k0;
-    if (lane + 32 < n && r1 < kKeep) keys[r1] = k1;
+    const unsigned long long k1 = has1 ? keys[lane + 32] : 0ull;
+    const int pos = __popc(__ballot_sync(kFull, k0 > x)) + __popc(__ballot_sync(kFull, has1 && k1 > x));
+    if (lane >= pos && lane + 1 < kKeep) keys[lane + 1] = k0;
+    if (has1 && lane + 32 >= pos && lane + 33 < kKeep) keys[lane + 33] = k1;
+    if (lane == 0) keys[pos] = x;
     __syncwarp();
     return unorder_bits((uint32_t)(keys[kKeep - 1] >> 32));
 }
@@ -239,15 +231,12 @@ __device__ __forceinline__ void dump_chunk(uint32_t *dst, const uint32_t (&v)[32
 
 // Rare path, once per stage and warp: rows whose threshold was beaten ("owners")
 // are served one at a time.  The owner spills the chunks that hit to the warp's
-// scratch line; then all 32 lanes test one column each, and the passing ones are
-// appended to the row's pending area with a ballot/popc prefix.  A full pending
-// area triggers the merge and the leftovers are re-tested against the new
-// threshold.
-__device__ __forceinline__ void absorb_stage(const uint32_t (&v)[kChunks][32], unsigned hits, float &tau, int &cnt,
+// scratch line; then all 32 lanes test one column each and the passing columns
+// are inserted in index order.
+__device__ __forceinline__ void absorb_stage(const uint32_t (&v)[kChunks][32], unsigned hits, float &tau,
                                              long long base, long long n_d, unsigned long long *rows, int row0,
                                              uint32_t *scratch, int lane) {
     unsigned owners = __ballot_sync(kFull, hits != 0);
-    const unsigned lt = (1u << lane) - 1u;
     while (owners) {
         const int bl = __ffs(owners) - 1;
         owners &= owners - 1;
@@ -259,29 +248,20 @@ __device__ __forceinline__ void absorb_stage(const uint32_t (&v)[kChunks][32], u
         }
         __syncwarp();
         float tb = __shfl_sync(kFull, tau, bl);
-        int cb = __shfl_sync(kFull, cnt, bl);
         unsigned long long *keys = rows + (size_t)(row0 + bl) * kCap;
         for (int c = 0; c < kChunks; ++c) {
             if (!(hb >> c & 1)) continue;
             const float x = __uint_as_float(scratch[32 * c + lane]);
-            const long long id = base + 32 * c + lane;
-            bool pend = x > tb && id < n_d;
-            for (;;) {
-                const unsigned pm = __ballot_sync(kFull, pend);
-                if (!pm) break;
-                const int room = kPend - cb, total = __popc(pm), pos = __popc(pm & lt);
-                if (pend && pos < room) {
-                    keys[kKeep + cb + pos] = make_key(x, (int)id);
-                    pend = false;
-                }
-                if (total <= room) { cb += total; break; }
-                __syncwarp();
-                tb = merge_row(keys, kPend, lane);       // pending area is full
-                cb = 0;
-                pend = pend && x > tb;
+            const long long id0 = base + 32 * c;
+            unsigned pm = __ballot_sync(kFull, x > tb && id0 + lane < n_d);
+            while (pm) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const float xs = __shfl_sync(kFull, x, j);
+                if (xs > tb) tb = insert_sorted(keys, make_key(xs, (int)(id0 + j)), lane);
             }
         }
-        if (lane == bl) { tau = tb; cnt = cb; }
+        if (lane == bl) tau = tb;
         __syncwarp();
     }
 }
@@ -338,6 +318,11 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const long long n_tiles = (n_d + kDTile - 1) / kDTile;
+    // Stages are visited starting at the CTA's own rows and wrapping around: when the
+    // queries are rows of the same table (the reference's aliasing) their best matches
+    // sit next to them, so the thresholds tighten within the first few stages.
+    // Neighbouring CTAs start two stages apart, so they still share every stage in L2.
+    const long long t_first = (q_base / kDTile) % n_tiles;
 
     if (warp == 8) {
         // ===== producer: bulk copies (TMA engine) =====
@@ -349,7 +334,8 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
-                bulk_g2s(smem_u32(smem + kOffB + s * kTileBytes), e_tiles + t * (kTileBytes / 16), kTileBytes,
+                const long long tt = (t + t_first) % n_tiles;
+                bulk_g2s(smem_u32(smem + kOffB + s * kTileBytes), e_tiles + tt * (kTileBytes / 16), kTileBytes,
                          bar_full + 8 * s);
             }
         }
@@ -393,7 +379,6 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
         const long long q = q_base + row0 + lane;
         float tau = (q < n_q && (!active || active[q])) ? -INFINITY : INFINITY;
         if (dbg & 4) tau = INFINITY;      // profiling aid: fast path only
-        int cnt = 0;
         uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + kOffScratch) + warp * kDTile;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
         for (long long t = 0; t < n_tiles; ++t) {
@@ -418,14 +403,9 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) hits |= (chunk_max(v[c]) > tau ? 1u : 0u) << c;
             if (__any_sync(kFull, hits != 0))
-                absorb_stage(v, hits, tau, cnt, t * kDTile, n_d, rows, row0, scratch, lane);
+                absorb_stage(v, hits, tau, ((t + t_first) % n_tiles) * kDTile, n_d, rows, row0, scratch, lane);
         }
-        // ---- fold the last pending candidates in, then exact float32 re-score and write-out ----
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            const int cr = __shfl_sync(kFull, cnt, r);
-            if (cr > 0) merge_row(rows + (size_t)(row0 + r) * kCap, cr, lane);
-        }
+        // ---- exact float32 re-score of the kept candidates and best-first write-out ----
         __syncwarp();
         for (int r = 0; r < 32; ++r) {
             const long long qq = q_base + row0 + r;
