@@ -202,6 +202,18 @@ int fwav_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_domains, const 
                               fwav_stream(ctx, stream));
 }
 
+int fwav_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_domains, const int32_t *d_idx,
+                     const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_ranges, int range_size,
+                     double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
+                     double *d_sums, void *stream) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, d_sums && (n_ranges == 0 || (d_domains && d_idx && d_s && d_o && d_sym && d_next)),
+                 "null buffer");
+    FWAV_REQUIRE(ctx, first || n_ranges == 0 || d_cur, "d_cur is required after the first iteration");
+    return fwav_launch_decode_iter(ctx, d_domains, n_domains, d_idx, d_s, d_o, d_sym, n_ranges, range_size,
+                                   s_clip, s_damping, first, d_cur, d_next, d_sums, fwav_stream(ctx, stream));
+}
+
 int fwav_compress_device(fwav_ctx *ctx, const float *d_signal, int64_t n_samples, const float *d_ranges,
                          int64_t n_ranges, int64_t query_offset, int tile_size, int emb_dim, int top_k,
                          double energy_thresh, int fast_mode, int query_mode, int build, float *d_domains,

@@ -89,6 +89,11 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
                        int iterations, double eps, double s_clip, double s_damping, float *d_out,
                        int *iters_run, float *last_delta, cudaStream_t st);
 
+int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
+                            const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
+                            double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
+                            double *d_sums, cudaStream_t st);
+
 #if defined(__CUDACC__)
 // streaming loads/stores that do not pollute L1 (data touched once)
 __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {

@@ -139,7 +139,60 @@ decode_select_kernel(const DecodeState *__restrict__ state, const T *__restrict_
         out[i] = scratch[i];
 }
 
+// sums the per-block partials of one iteration in index order into out[0..1]
+__global__ void __launch_bounds__(32)
+decode_sum_partials_kernel(const double *__restrict__ partials, int n_blocks, double *__restrict__ out) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n_blocks; i += 32) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_down_sync(kFull, a, off);
+        b += __shfl_down_sync(kFull, b, off);
+    }
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
 }  // namespace
+
+// One decoder iteration over a slice of ranges (multi-GPU decode: every rank owns a
+// slice, the two float64 sums are combined across ranks by the caller).
+int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
+                            const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
+                            double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
+                            double *d_sums, cudaStream_t st) {
+    FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
+    if (n_r == 0) {
+        FWAV_CUDA(ctx, cudaMemsetAsync(d_sums, 0, 2 * sizeof(double), st));
+        return FWAV_OK;
+    }
+    FWAV_REQUIRE(ctx, n_d >= 1, "decoder needs at least one domain row");
+    long long need = (n_r + kThreads - 1) / kThreads;
+    long long cap = (long long)ctx->num_sms * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    double *d_part = nullptr;
+    int rc = fwav_ws_reserve(ctx, WS_DECODE_RED, sizeof(double) * 2 * (size_t)cap + sizeof(DecodeState), (void **)&d_part);
+    if (rc) return rc;
+    DecodeState *d_state = reinterpret_cast<DecodeState *>(d_part + 2 * (size_t)cap);
+    FWAV_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(DecodeState), st));
+    const float clipf = (float)fabs(s_clip);
+    const int damped = s_damping > 0 ? 1 : 0;
+    const float omd = (float)(1.0 - s_damping), dmp = (float)s_damping;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_domains) | reinterpret_cast<uintptr_t>(d_cur) |
+                           reinterpret_cast<uintptr_t>(d_next)) & 15) == 0;
+#define FWAV_DEC(NT)                                                                                   \
+    decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
+                                                      damped, omd, dmp, first, d_cur, d_next, d_state, d_part)
+    if (aligned && N == 4) FWAV_DEC(4);
+    else if (aligned && N == 8) FWAV_DEC(8);
+    else if (aligned && N == 16) FWAV_DEC(16);
+    else if (aligned && N == 32) FWAV_DEC(32);
+    else FWAV_DEC(0);
+#undef FWAV_DEC
+    FWAV_LAUNCH_CHECK(ctx);
+    decode_sum_partials_kernel<<<1, 32, 0, st>>>(d_part, grid, d_sums);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
 
 int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
                        const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
@@ -164,9 +217,9 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
     double *d_part = nullptr;
     int rc = fwav_ws_reserve(ctx, WS_DECODE_A, sizeof(float) * (size_t)total, (void **)&d_scratch);
     if (rc) return rc;
-    rc = fwav_ws_reserve(ctx, WS_DECODE_RED, sizeof(double) * 2 * (size_t)grid + sizeof(DecodeState), (void **)&d_part);
+    rc = fwav_ws_reserve(ctx, WS_DECODE_RED, sizeof(double) * 2 * (size_t)cap + sizeof(DecodeState), (void **)&d_part);
     if (rc) return rc;
-    DecodeState *d_state = reinterpret_cast<DecodeState *>(d_part + 2 * (size_t)grid);
+    DecodeState *d_state = reinterpret_cast<DecodeState *>(d_part + 2 * (size_t)cap);
     FWAV_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(DecodeState), st));
 
     const float clipf = (float)fabs(s_clip);

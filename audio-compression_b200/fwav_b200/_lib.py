@@ -49,6 +49,8 @@ SIGNATURES = [
     ("fwav_decode", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int, C.c_int,
                               C.c_double, C.c_double, C.c_double, c_ptr,
                               C.POINTER(C.c_int), C.POINTER(C.c_float), c_ptr]),
+    ("fwav_decode_iter", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int,
+                                   C.c_double, C.c_double, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     ("fwav_compress_device", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, i64, C.c_int, C.c_int, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -255,6 +257,12 @@ class Context:
                                          int(iterations), float(convergence_eps), float(s_clip),
                                          float(s_damping), d_out, C.byref(it), C.byref(delta), stream))
         return it.value, delta.value
+
+    def decode_iter(self, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size, s_clip, s_damping,
+                    first, d_cur, d_next, d_sums, stream=None):
+        self._check(self.lib.fwav_decode_iter(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
+                                              float(s_clip), float(s_damping), int(bool(first)), d_cur, d_next,
+                                              d_sums, stream))
 
     def compress_device(self, d_signal, n, d_ranges, n_r, query_offset, tile_size, emb_dim, top_k,
                         energy_thresh, fast_mode, query_mode, build, d_domains, d_emb,

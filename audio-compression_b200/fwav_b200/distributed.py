@@ -1,0 +1,213 @@
+"""Range-sharded multi-GPU compress and decode.
+
+One process per GPU, `torch.distributed` for the plumbing (NCCL over NVLink on
+the B200 box; the host logic is backend-agnostic and is exercised with gloo,
+world_size 2, in tests/test_distributed_gloo.py).
+
+Compress (reference: np.array_split of the ranges over cpu_workers,
+fractal.py:1180-1207):
+    rank 0 builds the domain table and its embeddings, both are broadcast, every
+    rank matches its contiguous slice of ranges against the full tables, the five
+    match arrays are all-gathered.  No collective sits inside the search.
+
+Decode (reference loop fractal.py:1411-1467, range-local by construction):
+    every rank iterates its slice; per iteration the two float64 sums behind
+    delta are all-gathered and added in RANK ORDER (bit-stable for a given world
+    size), so all ranks take the same convergence decision; the reconstruction is
+    all-gathered every iteration (what BASELINE.json's north star specifies) or
+    once at the end (`gather_every_iteration=False`).
+
+The device work goes through an "engine" with four methods so the same driver
+runs on the CUDA library (CudaEngine, below) and, in the CPU tests, on a stand-in
+built from the oracle:
+    build_tables(signal, tile) -> (domains, embs)
+    match_slice(ranges, lo, hi, domains, embs, ...) -> (idx, s, o, err, sym) tensors
+    decode_iter(domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt) -> sums(2,) f64
+    empty(shape, dtype) / from_numpy(...) for allocation on the engine's device
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n, world):
+    """Contiguous slices with np.array_split's sizes (fractal.py:1182)."""
+    base, extra = divmod(int(n), int(world))
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    edges = np.concatenate([[0], np.cumsum(sizes)])
+    return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
+
+
+def delta_from_sums(dsq, csq):
+    """fractal.py:1460-1461 from float64 sums of squares, in float32 like numpy's norms."""
+    nd = np.float32(np.sqrt(np.float64(dsq)))
+    nc = np.float32(np.sqrt(np.float64(csq)))
+    return float(nd / (nc if nc > 0 else np.float32(1.0)))
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def compress_sharded(engine, signal, ranges, tile_size, emb_dim=16, top_k=32, energy_thresh=1e-4,
+                     fast_mode=True, query_mode=0, broadcast_tables=True):
+    """Returns (idx, s, o, sym, err, domains) as engine tensors on every rank."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n_r = ranges.shape[0]
+    bounds = shard_bounds(n_r, world)
+    lo, hi = bounds[rank]
+    if world > 1 and broadcast_tables:
+        domains, embs = engine.alloc_tables(signal, tile_size, emb_dim)
+        if rank == 0:
+            engine.build_tables(signal, tile_size, emb_dim, out=(domains, embs))
+        dist.broadcast(domains, 0)
+        dist.broadcast(embs, 0)
+    else:
+        domains, embs = engine.build_tables(signal, tile_size, emb_dim)
+    if query_mode == 0 and n_r > domains.shape[0]:
+        raise ValueError("mmap length is greater than file size")       # fractal.py:1190
+    part = engine.match_slice(ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh,
+                              fast_mode, query_mode)
+    if world == 1:
+        idx, s, o, err, sym = part
+        return idx, s, o, sym, err, domains
+    cap = max(b - a for a, b in bounds)
+    packed = engine.empty((4, cap), torch.int32)
+    packed.zero_()
+    for row, t in enumerate(part[:4]):
+        packed[row, :hi - lo] = t.view(torch.int32)
+    sym = engine.empty((cap,), torch.uint8)
+    sym.zero_()
+    sym[:hi - lo] = part[4]
+    # flat buffers: accepted by both the NCCL and the gloo all-gather
+    g32 = engine.empty((world * 4 * cap,), torch.int32)
+    gsym = engine.empty((world * cap,), torch.uint8)
+    dist.all_gather_into_tensor(g32, packed.view(-1))
+    dist.all_gather_into_tensor(gsym, sym)
+    g32, gsym = g32.view(world, 4, cap), gsym.view(world, cap)
+    cols = [torch.cat([g32[r, k, :b - a] for r, (a, b) in enumerate(bounds)]) for k in range(4)]
+    sym_all = torch.cat([gsym[r, :b - a] for r, (a, b) in enumerate(bounds)])
+    return (cols[0], cols[1].view(torch.float32), cols[2].view(torch.float32), sym_all,
+            cols[3].view(torch.float32), domains)
+
+
+def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, convergence_eps=1e-3,
+                   s_clip=16.0, s_damping=0.0, gather_every_iteration=True):
+    """Every rank passes the FULL match arrays; returns (recon tensor of
+    n_ranges*range_size on every rank, iterations run, last delta)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n_r, N = idx.shape[0], range_size
+    bounds = shard_bounds(n_r, world)
+    lo, hi = bounds[rank]
+    cap = max(b - a for a, b in bounds)
+    cur = engine.empty((cap * N,), torch.float32)
+    nxt = engine.empty((cap * N,), torch.float32)
+    cur.zero_()
+    nxt.zero_()
+    full = engine.empty((world * cap * N,), torch.float32) if world > 1 else None
+    all_sums = engine.empty((world * 2,), torch.float64)
+    it_run, delta = 0, 0.0
+    for it in range(iterations):
+        sums = engine.decode_iter(domains, idx[lo:hi], s[lo:hi], o[lo:hi], sym[lo:hi], N, s_clip, s_damping,
+                                  it == 0, cur, nxt)
+        if world > 1:
+            dist.all_gather_into_tensor(all_sums, sums)
+            if gather_every_iteration:
+                dist.all_gather_into_tensor(full, nxt)
+        else:
+            all_sums.copy_(sums)
+        host = all_sums.cpu().numpy().reshape(world, 2)
+        dsq = csq = 0.0
+        for r in range(world):                      # rank order: bit-stable for a given world size
+            dsq += float(host[r, 0])
+            csq += float(host[r, 1])
+        delta = delta_from_sums(dsq, csq)
+        cur, nxt = nxt, cur
+        it_run = it + 1
+        if delta < convergence_eps:
+            break
+    if world == 1:
+        return cur[:n_r * N], it_run, delta
+    if not gather_every_iteration or it_run == 0:
+        dist.all_gather_into_tensor(full, cur)
+    full = full.view(world, cap * N)
+    out = torch.cat([full[r, :(b - a) * N] for r, (a, b) in enumerate(bounds)])
+    return out, it_run, delta
+
+
+class CudaEngine:
+    """The engine on libfwav_b200.so: torch tensors for memory, the C ABI for work."""
+
+    def __init__(self, device):
+        import torch
+        from . import _lib
+        self.torch = torch
+        self.lib = _lib
+        self.device = torch.device("cuda", device)
+        self.ctx = _lib.Context(device)
+        self._sums = None
+
+    def _stream(self):
+        # torch's NULL stream is the legacy default stream; the C ABI reads NULL as "the
+        # context's own stream", so name the legacy stream explicitly (cudaStreamLegacy = 0x1)
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        return st if st else 1
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self.device)
+
+    def from_numpy(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def alloc_tables(self, signal, tile_size, emb_dim):
+        N, ds = self.lib.geometry(tile_size)
+        n_d = self.lib.count_domains(signal.shape[0], tile_size, ds)
+        return (self.empty((n_d, N), self.torch.float32), self.empty((n_d, emb_dim), self.torch.float32))
+
+    def build_tables(self, signal, tile_size, emb_dim, out=None):
+        N, ds = self.lib.geometry(tile_size)
+        domains, embs = out if out is not None else self.alloc_tables(signal, tile_size, emb_dim)
+        n_d = domains.shape[0]
+        self.ctx.build_domains(signal.data_ptr(), signal.shape[0], tile_size, N, ds, domains.data_ptr(), self._stream())
+        self.ctx.embed(domains.data_ptr(), n_d, N, emb_dim, embs.data_ptr(), self._stream())
+        return domains, embs
+
+    def match_slice(self, ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode,
+                    query_mode):
+        t = self.torch
+        N = ranges.shape[1]
+        cnt = hi - lo
+        idx = self.empty((cnt,), t.int32)
+        s, o, err = (self.empty((cnt,), t.float32) for _ in range(3))
+        sym = self.empty((cnt,), t.uint8)
+        if cnt:
+            rp = ranges.data_ptr() + lo * N * 4
+            act = self.empty((cnt,), t.uint8)
+            cand = self.empty((cnt, top_k), t.int32)
+            st = self._stream()
+            self.ctx.range_activity(rp, cnt, N, energy_thresh, fast_mode, act.data_ptr(), st)
+            if query_mode == 0:
+                qp = embs.data_ptr() + lo * emb_dim * 4
+            else:
+                q = self.empty((cnt, emb_dim), t.float32)
+                self.ctx.embed(rp, cnt, N, emb_dim, q.data_ptr(), st)
+                qp = q.data_ptr()
+            self.ctx.topk(qp, cnt, embs.data_ptr(), embs.shape[0], emb_dim, top_k, act.data_ptr(), cand.data_ptr(),
+                          None, st)
+            self.ctx.affine_match(rp, cnt, N, domains.data_ptr(), domains.shape[0], cand.data_ptr(), top_k, 16.0,
+                                  idx.data_ptr(), s.data_ptr(), o.data_ptr(), sym.data_ptr(), err.data_ptr(), st)
+        return idx, s, o, err, sym
+
+    def decode_iter(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt):
+        sums = self.empty((2,), self.torch.float64)
+        self.ctx.decode_iter(domains.data_ptr(), domains.shape[0], idx.data_ptr(), s.data_ptr(), o.data_ptr(),
+                             sym.data_ptr(), idx.shape[0], N, s_clip, s_damping, first, cur.data_ptr(),
+                             nxt.data_ptr(), sums.data_ptr(), self._stream())
+        return sums

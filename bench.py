@@ -361,8 +361,10 @@ def run_ours(args):
 
     # ---- decode leg: config-5-shaped synthetic matches on this rank ----
     decode = None
-    if rank == 0 and not args.no_decode:
+    if world == 1 and not args.no_decode:
         decode = run_decode(ctx, torch, dev, peaks, args)
+    elif world > 1 and not args.no_decode:
+        decode = run_decode_sharded(torch, dist, dev, local, peaks, args)
 
     # ---- CPU baseline (oracle port), rank 0, N == 1 only ----
     cpu = None
@@ -485,6 +487,47 @@ def run_decode(ctx, torch, dev, peaks, args):
     res["config"] = {"workload": f"c5-shaped: {n_r} ranges x {N} samples, {n_d} domain rows, synthetic matches, "
                                  f"{iters} iterations, convergence_eps=0 (inputs resident in HBM; "
                                  f"{(12 * N + 13) * n_r / 1e9:.2f} GB/iter > L2)"}
+    return res
+
+
+def run_decode_sharded(torch, dist, dev, local, peaks, args):
+    """Config 5 shape sharded by ranges over the ranks (fwav_b200.distributed): per
+    iteration a 2-double all-gather for delta, plus the all-gather of the
+    reconstruction either every iteration (north star) or once at the end."""
+    from fwav_b200 import distributed as D
+    world, rank = dist.get_world_size(), dist.get_rank()
+    N = 16
+    n_r = int(10_800_000 * args.decode_scale)
+    n_d = int(43_198_977 * args.decode_scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)                      # same seed on every rank: identical replicated inputs
+    domains = torch.randn((n_d, N), generator=g, device=dev, dtype=torch.float32) * 300
+    idx = torch.randint(0, n_d, (n_r,), generator=g, device=dev, dtype=torch.int32)
+    s = (torch.rand(n_r, generator=g, device=dev) * 2 - 1).float()
+    o = (torch.rand(n_r, generator=g, device=dev) * 2000 - 1000).float()
+    sym = torch.randint(0, 2, (n_r,), generator=g, device=dev, dtype=torch.uint8)
+    eng = D.CudaEngine(local)
+    iters = 32
+    res = {}
+    for tag, every in (("allgather_every_iteration", True), ("allgather_once", False)):
+        ms = []
+        for rep in range(3):
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out, it, delta = D.decode_sharded(eng, domains, idx, s, o, sym, N, iterations=iters,
+                                              convergence_eps=0.0, s_damping=0.5, gather_every_iteration=every)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per_iter = float(t[0]) / it
+        res[tag] = {"value": n_r * N / (per_iter * 1e-3) / 1e6, "unit": "Msamples/s/iter", "iterations": it,
+                    "ms_per_iter": per_iter, "allgather_bytes_per_iter": int(4 * n_r * N) if every else 0}
+    res["config"] = {"workload": f"c5-shaped: {n_r} ranges x {N} samples sharded over {world} ranks, {n_d} domain rows "
+                                 f"replicated, synthetic matches, {iters} iterations, eps=0, s_damping=0.5"}
     return res
 
 

@@ -116,6 +116,17 @@ int fwav_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
                 double s_clip, double s_damping, float *d_out,
                 int *iters_run, float *last_delta, void *stream);
 
+/* One iteration of the same loop over a slice of ranges, for range-sharded
+ * multi-GPU decoding: reads d_cur (ignored when first != 0: the reconstruction
+ * starts at zero, fractal.py:1389), writes d_next, and leaves
+ * d_sums[0] = sum (next-cur)^2, d_sums[1] = sum cur^2 (float64, fixed order) on
+ * the device.  Asynchronous; the caller combines the sums across ranks and
+ * applies the convergence test of fractal.py:1460-1467. */
+int fwav_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
+                     const int32_t *d_idx, const float *d_s, const float *d_o, const uint8_t *d_sym,
+                     int64_t n_ranges, int range_size, double s_clip, double s_damping, int first,
+                     const float *d_cur, float *d_next, double *d_sums, void *stream);
+
 /* Device pipeline A1..A7 on resident inputs: replaces the process/queue
  * pipeline of compress_audio (fractal.py:1114-1245) between "ranges framed"
  * and "matches collected".  d_signal is the raw signal (domains are built

@@ -396,3 +396,32 @@ def test_decode_properties(ctx):
     want = O.decode(idx[:5000], s[:5000], o[:5000], sym[:5000], domains, 5000, N, iterations=6,
                     convergence_eps=0.0, s_damping=0.5)
     assert iters == 6 and np.array_equal(bits(out[:5000 * N]), bits(want))
+
+
+# ------------------------------------------------------------------ the multi-GPU driver on one GPU
+def test_cuda_engine_through_the_sharded_driver():
+    """fwav_b200.distributed with the real CUDA engine (world size 1: no process
+    group): same driver code the NCCL run uses, including fwav_decode_iter."""
+    import torch
+    from fwav_b200 import distributed as D
+    eng = D.CudaEngine(0)
+    for name in ("music_t4096", "sine_t1024", "gaps_t1024"):
+        g = golden(name)
+        N = int(g["range_size"])
+        sig, rng = eng.from_numpy(g["signal"]), eng.from_numpy(g["ranges"])
+        idx, s, o, sym, err, dom = D.compress_sharded(eng, sig, rng, int(g["tile_size"]), 16, int(g["top_k"]), 1e-4)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(dom.cpu().numpy()), bits(g["domains"]))
+        res = dict(idx=idx.cpu().numpy(), s=s.cpu().numpy(), o=o.cpu().numpy(), sym=sym.cpu().numpy(),
+                   err=err.cpu().numpy())
+        st = classify_matches(res, g, int(g["top_k"]))
+        assert st["boundary"] <= st["ambiguous"], st
+        gi, gs, go, gy = (eng.from_numpy(g[k]) for k in ("idx", "s", "o", "sym"))
+        gd = eng.from_numpy(g["domains"])
+        for tag, kw in DECODES.items():
+            rec, iters, delta = D.decode_sharded(eng, gd, gi, gs, go, gy, N, **kw)
+            want = g["dec_" + tag]
+            assert np.array_equal(bits(rec.cpu().numpy()[:len(want)]), bits(want)), (name, tag)
+            _, trace = O.decode(g["idx"], g["s"], g["o"], g["sym"], g["domains"], len(g["idx"]), N,
+                                want_trace=True, **kw)
+            assert iters == len(trace)
