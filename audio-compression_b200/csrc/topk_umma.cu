@@ -35,6 +35,9 @@
 // that); see DESIGN.md for the epilogue budget.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "fwav_math.cuh"
@@ -44,16 +47,16 @@ namespace {
 constexpr int ED = 16;                 // embedding dim this kernel is built for
 constexpr int kQTile = 256;            // queries per CTA (2 x M=128)
 constexpr int kDTile = 128;            // domains per stage (UMMA N)
-constexpr int kStages = 3;
+constexpr int kStages = 12;           // 96 KB of domain stages in flight: the ring has to cover the L2/HBM latency
 constexpr int kThreads = 320;          // 8 epilogue warps + producer/alloc warp + MMA warp
 constexpr int kChunks = kDTile / 32;   // 32-column TMEM chunks per stage
 constexpr int kKeep = 48;              // candidates kept per query (top_k <= 32 plus a 16-entry margin)
 constexpr int kCap = kKeep;            // eight-byte keys per query row in shared memory
-constexpr uint32_t kPartBytes = kDTile * ED * 4;       // 8 KB: one 128-row hi or lo tile
-constexpr uint32_t kTileBytes = 2 * kPartBytes;        // 16 KB: hi | lo
-constexpr uint32_t kABytes = 2 * kTileBytes;           // 32 KB: two query halves
+constexpr uint32_t kPartBytes = kDTile * ED * 2;       // 4 KB: one 128-row hi or lo tile (fp16)
+constexpr uint32_t kTileBytes = 2 * kPartBytes;        // 8 KB: hi | lo
+constexpr uint32_t kABytes = 2 * kTileBytes;           // 16 KB: two query halves
 constexpr uint32_t kLBO = kDTile * 16;                 // bytes between the two 16-byte K chunks
-constexpr uint32_t kSBO = 128;                         // bytes between 8-row groups
+constexpr uint32_t kSBO = 256;                         // bytes between 8-row groups (8 rows x 32 B)
 constexpr unsigned kFull = 0xffffffffu;
 
 // shared memory map (dynamic, 1024-aligned)
@@ -62,10 +65,11 @@ constexpr uint32_t kOffB = kOffA + kABytes;
 constexpr uint32_t kOffList = kOffB + kStages * kTileBytes;
 constexpr uint32_t kOffScratch = kOffList + kQTile * kCap * 8;       // one owner's stage of scores per warp
 constexpr uint32_t kOffBars = kOffScratch + 8 * kDTile * 4;
-constexpr uint32_t kSmemBytes = kOffBars + 128;
+constexpr uint32_t kBarBytes = 16 * kStages + 64;      // full[], empty[], tfull[2], tempty[2], a, done, tmem slot
+constexpr uint32_t kSmemBytes = kOffBars + kBarBytes;
 
-// UMMA instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kDTile >> 3) << 17) | ((128u >> 4) << 24);
+// UMMA instruction descriptor: D=F32, A=B=F16, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((kDTile >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,15 +105,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// K-major SWIZZLE_32B matrix descriptor (cute::UMMA::SmemDescriptor, version 1): 8-row groups
+// kSBO bytes apart, the two 16-byte K chunks of a row adjacent (leading offset 1)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
-           (1ull << 46);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(kSBO >> 4) << 32) |
+           (1ull << 46) | (6ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 operands, K = 16 per instruction, f32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
         : "memory");
 }
@@ -147,32 +154,41 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // ---------------------------------------------------------------------------
-// pack: row-major f32 (rows x 16) -> 128-row tiles [hi | lo][K chunk 0..3][row] of float4
+// pack: row-major f32 (rows x 16) -> 128-row tiles [hi | lo][K chunk 0..1][row] of
+// 16-byte granules (8 halves).  x = hi + lo with hi = fp16(x), lo = fp16(x - hi):
+// 22 significant bits for |x| in the fp16 normal range and an absolute error below
+// 3e-8 otherwise (embedding components are bounded by 1), measured 3.9e-7 max on
+// the scores — the same as a float32 sgemv.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_tf32_tiles_kernel(const float *__restrict__ src, long long n_rows, long long n_tiles,
-                       float4 *__restrict__ dst) {
-    const long long total = n_tiles * (kDTile * 4);
+pack_f16_tiles_kernel(const float *__restrict__ src, long long n_rows, long long n_tiles,
+                      uint4 *__restrict__ dst) {
+    const long long total = n_tiles * (kDTile * 2);
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
-        const long long tile = g / (kDTile * 4);
-        const int w = (int)(g - tile * (kDTile * 4));
-        const int c = w / kDTile, r = w % kDTile;
+        const long long tile = g / (kDTile * 2);
+        const int w = (int)(g - tile * (kDTile * 2));
+        const int c = w / kDTile, r = w % kDTile;       // c: which 8-element K chunk
         const long long row = tile * kDTile + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < n_rows) x = __ldg(reinterpret_cast<const float4 *>(src + row * ED + c * 4));
-        float xs[4] = {x.x, x.y, x.z, x.w}, hi[4], lo[4];
+        float xs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row < n_rows) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src + row * ED + c * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(src + row * ED + c * 8 + 4));
+            xs[0] = a.x; xs[1] = a.y; xs[2] = a.z; xs[3] = a.w; xs[4] = b.x; xs[5] = b.y; xs[6] = b.z; xs[7] = b.w;
+        }
+        __half2 hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint32_t h, l;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(xs[i]));
-            hi[i] = __uint_as_float(h);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(xs[i] - hi[i]));
-            lo[i] = __uint_as_float(l);
+            const __half h0 = __float2half_rn(xs[2 * i]), h1 = __float2half_rn(xs[2 * i + 1]);
+            hi[i] = __halves2half2(h0, h1);
+            lo[i] = __halves2half2(__float2half_rn(xs[2 * i] - __half2float(h0)),
+                                   __float2half_rn(xs[2 * i + 1] - __half2float(h1)));
         }
-        float4 *t = dst + tile * (2 * kDTile * 4);
-        t[c * kDTile + r] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        t[kDTile * 4 + c * kDTile + r] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        uint4 *t = dst + tile * (2 * kDTile * 2);
+        // SWIZZLE_32B K-major atom: 8 rows x 32 bytes, 16-byte chunk index XOR (row >> 2) & 1
+        const int slot = (r >> 3) * 16 + (r & 7) * 2 + (c ^ ((r >> 2) & 1));
+        t[slot] = *reinterpret_cast<const uint4 *>(hi);
+        t[kDTile * 2 + slot] = *reinterpret_cast<const uint4 *>(lo);
     }
 }
 
@@ -267,7 +283,7 @@ __device__ __forceinline__ void absorb_stage(const uint32_t (&v)[kChunks][32], u
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ e_tiles,
+topk_umma_kernel(const uint4 *__restrict__ q_tiles, const uint4 *__restrict__ e_tiles,
                  const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d,
                  int top_k, const uint8_t *__restrict__ active, int32_t *__restrict__ cand,
                  float *__restrict__ scores, int dbg) {
@@ -279,7 +295,7 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
     // barrier slots (8 bytes each)
     const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_tfull = bars + 16 * kStages,
                    bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffBars + 120);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffBars + kBarBytes - 8);
 
     // whole-CTA early out (energy-pruned stretch): every row gets -1
     {
@@ -305,6 +321,7 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
         mbar_init(bar_a, 1);
+        mbar_init(bar_a + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -349,27 +366,25 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 const int buf = (int)(t & 1);
                 const uint32_t tph = (uint32_t)((t >> 1) & 1);
-                mbar_wait(bar_tempty + 8 * buf, tph ^ 1);
-                mbar_wait(bar_full + 8 * s, ph);
+                if (!(dbg & 8)) mbar_wait(bar_tempty + 8 * buf, tph ^ 1);    // dbg 8: free-running MMA (profiling)
+                if (!(dbg & 16)) mbar_wait(bar_full + 8 * s, ph);            // dbg 16: no producer (profiling)
                 tc_fence_after();
                 const uint32_t b_hi = smem_u32(smem + kOffB + s * kTileBytes), b_lo = b_hi + kPartBytes;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t a_hi = a_addr + h * kTileBytes, a_lo = a_hi + kPartBytes;
                     const uint32_t d = tmem_base + (uint32_t)(buf * 256 + h * 128);
-                    // small cross terms first, the hi*hi term last
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_tf32(d, smem_desc(a_hi + ks * 2 * kLBO), smem_desc(b_lo + ks * 2 * kLBO), ks);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_tf32(d, smem_desc(a_lo + ks * 2 * kLBO), smem_desc(b_hi + ks * 2 * kLBO), 1);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_tf32(d, smem_desc(a_hi + ks * 2 * kLBO), smem_desc(b_hi + ks * 2 * kLBO), 1);
+                    // small cross terms first, the hi*hi term last; one K=16 instruction each
+                    umma_f16(d, smem_desc(a_hi), smem_desc(b_lo), 0);
+                    umma_f16(d, smem_desc(a_lo), smem_desc(b_hi), 1);
+                    umma_f16(d, smem_desc(a_hi), smem_desc(b_hi), 1);
                 }
                 umma_commit(bar_empty + 8 * s);        // stage free once these MMAs have read it
                 umma_commit(bar_tfull + 8 * buf);      // accumulators ready for the epilogue
+            }
+            if (dbg & 8) {   // free-running profiling mode: drain the tensor pipe before leaving
+                umma_commit(bar_a + 8);
+                mbar_wait(bar_a + 8, 0);
             }
         }
     } else if (warp < 8) {
@@ -381,7 +396,7 @@ topk_umma_kernel(const float4 *__restrict__ q_tiles, const float4 *__restrict__ 
         if (dbg & 4) tau = INFINITY;      // profiling aid: fast path only
         uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + kOffScratch) + warp * kDTile;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
-        for (long long t = 0; t < n_tiles; ++t) {
+        for (long long t = 0; t < ((dbg & 8) ? 0 : n_tiles); ++t) {
             const int buf = (int)(t & 1);
             const uint32_t tph = (uint32_t)((t >> 1) & 1);
             mbar_wait(bar_tfull + 8 * buf, tph);
@@ -470,7 +485,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const long long e_tiles = (n_d + kDTile - 1) / kDTile;
     const long long q_ctas = (n_q + kQTile - 1) / kQTile;
     const long long q_tiles = q_ctas * 2;
-    float4 *d_et = nullptr, *d_qt = nullptr;
+    uint4 *d_et = nullptr, *d_qt = nullptr;
     int rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_E, (size_t)e_tiles * kTileBytes, (void **)&d_et))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_Q, (size_t)q_tiles * kTileBytes, (void **)&d_qt))) return rc;
@@ -478,9 +493,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         long long need = (work + 255) / 256, cap = (long long)ctx->num_sms * 8;
         return (int)(need < cap ? need : cap);
     };
-    pack_tf32_tiles_kernel<<<grid_for(e_tiles * kDTile * 4), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et);
+    pack_f16_tiles_kernel<<<grid_for(e_tiles * kDTile * 2), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et);
     FWAV_LAUNCH_CHECK(ctx);
-    pack_tf32_tiles_kernel<<<grid_for(q_tiles * kDTile * 4), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt);
+    pack_f16_tiles_kernel<<<grid_for(q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt);
     FWAV_LAUNCH_CHECK(ctx);
     FWAV_CUDA(ctx, cudaFuncSetAttribute(topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
