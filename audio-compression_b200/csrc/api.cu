@@ -111,6 +111,7 @@ int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl) {
 }
 
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx) { return ctx ? ctx->umma_fallback_queries : 0; }
 
 int fwav_geometry(int tile_size, int *range_size, int *domain_step) {
     const int rs = tile_size / 256 > 4 ? tile_size / 256 : 4;      // fractal.py:1070

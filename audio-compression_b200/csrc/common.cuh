@@ -18,6 +18,7 @@ struct fwav_ctx {
     char err[512] = {0};
     int search_impl = FWAV_SEARCH_AUTO;
     int64_t launches = 0;
+    int64_t umma_fallback_queries = 0;   // queries the fast search path handed to the exact list kernel
 
     // embedding matrices cached per (N, half)
     int emb_N = 0, emb_half = 0;
@@ -33,6 +34,7 @@ struct fwav_ctx {
 // scratch slots
 enum {
     WS_HALF = 0, WS_ACTIVE, WS_CAND, WS_QEMB, WS_DECODE_A, WS_DECODE_RED, WS_UMMA_E, WS_UMMA_Q, WS_UMMA_MISC,
+    WS_UMMA_THETA, WS_UMMA_CBUF, WS_UMMA_CNT, WS_UMMA_FAIL, WS_UMMA_FB, WS_UMMA_PARTS,
     // device mirrors of the host-buffer entry points
     WS_H_SIGNAL, WS_H_RANGES, WS_H_DOMAINS, WS_H_EMB, WS_H_MATCH, WS_H_OUT,
     WS_COUNT

@@ -46,6 +46,8 @@
 
 #include <cuda_fp16.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "fwav_math.cuh"
 
@@ -57,7 +59,13 @@ constexpr int kQPair = 2 * kQTile;     // queries per cluster
 constexpr int kDTile = 128;            // domain rows per packed tile = one CTA's half of a stage
 constexpr int kDStage = 2 * kDTile;    // domains per stage (UMMA N)
 constexpr int kStages = 8;             // 64 KB of domain tiles in flight per CTA (power of two)
-constexpr int kThreads = 352;          // warps 0-7 epilogue, 8 producer + TMEM alloc, 9-10 MMA issuers (leader) / 9 relay (peer)
+// Epilogue warps per CTA: 8 for MODE_LISTS (two per TMEM lane quadrant, 128 columns each: its lists need the shared
+// memory), 16 for the streaming modes (four per quadrant, 64 columns each).  An epilogue warp's stage is a serial chain
+// of long-latency operations (mbarrier wait ~90 cycles, tcgen05.ld + wait ~130, 38 half-rate max instructions, arrive);
+// measured with two warps per scheduler the chain takes ~1250 cycles a stage while the tensor pipe needs 490, so the
+// streaming modes put four warps on every scheduler to hide it.  Then: producer + TMEM alloc warp, two MMA issuer warps.
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == 0 ? 8 : 16; }
+__host__ __device__ constexpr int n_threads(int mode) { return (epi_warps(mode) + 3) * 32; }
 constexpr int kChunks = 4;             // 32-column TMEM chunks per warp and stage (128 columns)
 constexpr int kKeep = 48;              // candidates kept per query (top_k <= 32 plus a 16-entry margin)
 constexpr int kCap = kKeep;            // eight-byte keys per query row in shared memory
@@ -70,10 +78,41 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + kTileBytes;
 constexpr uint32_t kOffList = kOffB + kStages * kTileBytes;
-constexpr uint32_t kOffScratch = kOffList + kQTile * 2 * kCap * 8;   // [row][column half][kCap] keys; then one owner's 128 scores per warp
-constexpr uint32_t kOffBars = kOffScratch + 8 * 128 * 4;
+constexpr uint32_t kOffBars = kOffList;                 // barriers first, so that their place does not depend on the mode
 constexpr uint32_t kBarBytes = 16 * kStages + 72;      // full[], empty[], tfull[2], tempty[2], a, done[2], tmem slot
-constexpr uint32_t kSmemBytes = kOffBars + kBarBytes;
+constexpr uint32_t kOffMode = kOffBars + 256;          // mode-specific area
+// MODE_LISTS: [row][column half][kCap] keys, then one owner's 128 scores per warp
+constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
+constexpr uint32_t kSmemLists = kOffScratch + 8 * 128 * 4;
+// MODE_THETA: [row][kTheta] scores of column half 1 for the final merge of the two halves
+constexpr int kTheta = 16;             // threshold = kTheta-th largest score against the sample table
+constexpr int kThetaPart = 6;          // kept per column group (four groups per row)
+constexpr uint32_t kSmemTheta = kOffMode + kQTile * 3 * kThetaPart * 4;
+constexpr uint32_t kSmemCollect = kOffMode;
+static_assert(kBarBytes <= 256, "barrier block");
+
+enum { MODE_LISTS = 0, MODE_THETA = 1, MODE_COLLECT = 2 };
+
+struct ScanArgs {
+    const uint4 *q_tiles;      // packed query tiles (one per CTA)
+    const uint4 *e_tiles;      // packed domain tiles (two per stage)
+    const float *Q, *E;        // the float32 tables (exact re-score)
+    long long n_q, n_d;
+    int n_stages;              // stages in the table
+    int n_split;               // CTA pairs per 256 queries: each scans 1/n_split of the stages (MODE_LISTS: > 1 writes `parts`)
+    unsigned long long *parts; // MODE_LISTS, n_split > 1: [query][split][2 * kCap] tensor-core-score keys for merge_parts_kernel
+    int top_k;
+    const uint8_t *active;
+    int32_t *cand;             // MODE_LISTS out
+    float *scores;             // MODE_LISTS out (optional)
+    float *theta;              // MODE_THETA out, MODE_COLLECT in
+    int32_t *cbuf;             // MODE_COLLECT out: [query][column group][cap] domain indices
+    int *ccount;               // MODE_COLLECT out: [query][column group] how many passed (may exceed cap)
+    int cap;
+    int dbg;
+    long long *trace;          // profiling: clock64 stamps of pair 0's leader CTA, [stage][8] (dbg bit 64)
+};
+
 
 // UMMA instruction descriptor: D=F32, A=B=F16, both K-major, N=256, M=256 (cta_group::2)
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)(kQPair >> 4) << 24);
@@ -109,6 +148,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (spin > (1u << 22)) __trap();   // a lost arrival must fail loudly, never hang the GPU
     }
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -185,14 +235,21 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_f16_tiles_kernel(const float *__restrict__ src, long long n_rows, long long n_tiles,
-                      uint4 *__restrict__ dst) {
+                      uint4 *__restrict__ dst, int row_stride) {
     const long long total = n_tiles * (kDTile * 2);
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
         const long long tile = g / (kDTile * 2);
         const int w = (int)(g - tile * (kDTile * 2));
         const int c = w / kDTile, r = w % kDTile;       // c: which 8-element K chunk
-        const long long row = tile * kDTile + r;
+        long long row = tile * kDTile + r;
+        if (row_stride > 1) {
+            // the sample table of pass 1: every row_stride-th domain, dealt round-robin to the four 64-column
+            // groups of a stage, so that the neighbouring samples of one similarity peak do not all land in the
+            // same epilogue warp's column group (pass 1 needs no indices, any order will do)
+            const long long in_stage = row & (kDStage - 1);
+            row = ((row & ~(long long)(kDStage - 1)) + (in_stage & 63) * 4 + (in_stage >> 6)) * row_stride;
+        }
         float xs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (row < n_rows) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(src + row * ED + c * 8));
@@ -318,26 +375,86 @@ __device__ __forceinline__ void absorb_stage(const uint32_t (&v)[kChunks][32], u
     }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-topk_umma_kernel(const uint4 *__restrict__ q_tiles, const uint4 *__restrict__ e_tiles,
-                 const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d,
-                 int n_stages, int top_k, const uint8_t *__restrict__ active, int32_t *__restrict__ cand,
-                 float *__restrict__ scores, int dbg) {
+// insert x into a descending register list (compare-exchange chain, no memory)
+template <int L>
+__device__ __forceinline__ void insert_desc(float (&t)[L], float x) {
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const float hi = fmaxf(t[i], x);
+        x = fminf(t[i], x);
+        t[i] = hi;
+    }
+}
+
+// Visit the columns j of one 32-column chunk with v[j] >= thr, pruning with the same 3-input max
+// tree chunk_max uses (nine-column groups, then triples, then single columns): a chunk that holds
+// one short run of passing columns costs ~15 comparisons instead of 32.  f(j) is called per thread.
+template <class F>
+__device__ __forceinline__ void for_each_ge(const uint32_t (&v)[32], float thr, F f) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        float m[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            m[i] = max3(__uint_as_float(v[9 * g + 3 * i]), __uint_as_float(v[9 * g + 3 * i + 1]), __uint_as_float(v[9 * g + 3 * i + 2]));
+        if (max3(m[0], m[1], m[2]) >= thr) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (m[i] >= thr) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        if (__uint_as_float(v[9 * g + 3 * i + e]) >= thr) f(9 * g + 3 * i + e);
+                }
+            }
+        }
+    }
+    if (max3(__uint_as_float(v[27]), __uint_as_float(v[28]), __uint_as_float(v[29])) >= thr) {
+#pragma unroll
+        for (int e = 27; e < 30; ++e)
+            if (__uint_as_float(v[e]) >= thr) f(e);
+    }
+    if (__uint_as_float(v[30]) >= thr) f(30);
+    if (__uint_as_float(v[31]) >= thr) f(31);
+}
+
+// One kernel skeleton, three epilogues:
+//   MODE_LISTS    exact threshold top-K with sorted per-row lists in shared memory (any table; the
+//                 fallback of the fast path below and the path for small tables);
+//   MODE_THETA    pass 1 of the fast path: scans a packed sample of the table (every 16th domain) and
+//                 keeps, per row and in registers, the kTheta largest scores; theta = the kTheta-th of them, so about
+//                 16 * kTheta domains of the whole table reach it (Gamma(kTheta) spread: fewer than 32
+//                 with probability ~1e-8);
+//   MODE_COLLECT  pass 2: visits every stage with theta fixed and appends the index of every column
+//                 that reaches it to the row's buffer in global memory — no ordering work at all.
+constexpr int kTraceFrom = 256, kTraceStages = 64;
+#define FWAV_TRACE(slot, t)                                                                           \
+    do {                                                                                              \
+        if ((dbg & 64) && blockIdx.x == 0 && (t) >= kTraceFrom && (t) < kTraceFrom + kTraceStages)    \
+            a.trace[((t) - kTraceFrom) * 8 + (slot)] = clock64();                                     \
+    } while (0)
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+    constexpr int kEpi = epi_warps(MODE), kThreads = n_threads(MODE);
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_q = a.n_q, n_d = a.n_d;
+    const int top_k = a.top_k, dbg = a.dbg;
+    const uint8_t *__restrict__ active = a.active;
     uint32_t cta_rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-    const long long pair_base = (long long)(blockIdx.x >> 1) * kQPair;     // first query of the pair
+    const int pair_id = (int)(blockIdx.x >> 1) / a.n_split, split = (int)(blockIdx.x >> 1) % a.n_split;
+    const long long pair_base = (long long)pair_id * kQPair;               // first query of the pair
     const long long q_base = pair_base + (long long)cta_rank * kQTile;    // first query of this CTA
-    unsigned long long *rows = reinterpret_cast<unsigned long long *>(smem + kOffList);
+    unsigned long long *rows = reinterpret_cast<unsigned long long *>(smem + kOffMode);
     const uint32_t bars = smem_u32(smem + kOffBars);
     // barrier slots (8 bytes each)
     const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_tfull = bars + 16 * kStages,
                    bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kOffBars + kBarBytes - 8);
 
-    // whole-pair early out (energy-pruned stretch): every row gets -1.  Both CTAs look at all
-    // 256 rows so that they take the same decision.
+    // whole-pair early out (energy-pruned stretch).  Both CTAs look at all 256 rows so that they
+    // take the same decision.
     {
         int any = 0;
         for (int i = threadIdx.x; i < kQPair; i += kThreads) {
@@ -345,29 +462,41 @@ topk_umma_kernel(const uint4 *__restrict__ q_tiles, const uint4 *__restrict__ e_
             if (q < n_q && (!active || active[q])) any = 1;
         }
         if (!__syncthreads_or(any)) {
-            for (int i = threadIdx.x; i < kQTile * top_k; i += kThreads) {
-                const long long q = q_base + i / top_k;
-                if (q < n_q) {
-                    cand[q * top_k + i % top_k] = -1;
-                    if (scores) scores[q * top_k + i % top_k] = -INFINITY;
+            if (MODE == MODE_LISTS && a.n_split > 1) {
+                // merge_parts_kernel writes the -1 rows of pruned queries itself
+            } else if (MODE == MODE_LISTS) {
+                for (int i = threadIdx.x; i < kQTile * top_k; i += kThreads) {
+                    const long long q = q_base + i / top_k;
+                    if (q < n_q) {
+                        a.cand[q * top_k + i % top_k] = -1;
+                        if (a.scores) a.scores[q * top_k + i % top_k] = -INFINITY;
+                    }
+                }
+            } else {
+                for (int i = threadIdx.x; i < kQTile; i += kThreads) {
+                    const long long q = q_base + i;
+                    if (q >= n_q) continue;
+                    if (MODE == MODE_THETA) a.theta[q] = INFINITY;
+                    if (MODE == MODE_COLLECT) { for (int g = 0; g < 4; ++g) a.ccount[4 * q + g] = 0; }
                 }
             }
             return;
         }
     }
 
-    for (int i = threadIdx.x; i < kQTile * 2 * kCap; i += kThreads) rows[i] = empty_key(i % kCap);
+    if (MODE == MODE_LISTS)
+        for (int i = threadIdx.x; i < kQTile * 2 * kCap; i += kThreads) rows[i] = empty_key(i % kCap);
     if (threadIdx.x == 0) {
         // the leader's "stage has landed" barriers collect its own copy and the peer's relay
         const uint32_t n_land = cta_rank == 0 ? 2u : 1u;
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, n_land); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 16); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * kEpi); }
         mbar_init(bar_a, n_land);
         mbar_init(bar_a + 8, 1);
         mbar_init(bar_a + 16, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kEpi) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(512u)
                      : "memory");
@@ -378,161 +507,440 @@ topk_umma_kernel(const uint4 *__restrict__ q_tiles, const uint4 *__restrict__ e_
     cluster_sync_all();           // barriers of both CTAs are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // Stages are visited starting at the pair's own rows and wrapping around: when the
-    // queries are rows of the same table (the reference's aliasing) their best matches
-    // sit next to them, so the thresholds tighten within the first few stages.
-    // Neighbouring pairs start one stage apart, so they still share every stage in L2.
-    const int t_first = (int)((pair_base / kDStage) % n_stages);
+    // Full scans visit the stages starting at the pair's own rows and wrapping around: when the
+    // queries are rows of the same table (the reference's aliasing) their best matches sit next to
+    // them, so MODE_LISTS thresholds tighten within the first few stages; and neighbouring pairs
+    // are always one stage apart, so every stage is read from HBM once and from L2 by the rest.
+    // With n_split > 1 this pair only covers its share [s_lo, s_hi) of the stages.
+    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
+    const int n_visit = s_hi - s_lo;
+    const int t_first = s_lo + (int)((pair_base / kDStage) % n_visit);
 
-    if (warp == 8) {
+    if (warp == kEpi) {
         // ===== producer: bulk copies (TMA engine) of this CTA's query tile and its half of every stage =====
         if (lane == 0) {
             mbar_expect_tx(bar_a, kTileBytes);
-            bulk_g2s(smem_u32(smem + kOffA), q_tiles + ((long long)blockIdx.x) * (kTileBytes / 16), kTileBytes, bar_a);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (2ll * pair_id + cta_rank) * (kTileBytes / 16), kTileBytes, bar_a);
             int tt = t_first;
-            for (int t = 0; t < n_stages; ++t) {
+            for (int t = 0; t < n_visit; ++t) {
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
                 bulk_g2s(smem_u32(smem + kOffB + s * kTileBytes),
-                         e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kTileBytes, bar_full + 8 * s);
-                if (++tt == n_stages) tt = 0;
+                         a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kTileBytes, bar_full + 8 * s);
+                if (++tt == s_hi) tt = s_lo;
             }
         }
-    } else if (cta_rank != 0 && warp >= 9) {
+    } else if (cta_rank != 0 && warp > kEpi) {
         // ===== peer CTA: tell the leader when this CTA's operands have landed =====
-        if (warp == 9 && lane == 0) {
+        if (warp == kEpi + 1 && lane == 0) {
             mbar_wait(bar_a, 0);
             mbar_arrive_remote(bar_a, 0);
-            for (int t = 0; t < n_stages; ++t) {
+            for (int t = 0; t < n_visit; ++t) {
                 const int s = t & (kStages - 1);
                 mbar_wait(bar_full + 8 * s, (uint32_t)((t / kStages) & 1));
                 mbar_arrive_remote(bar_full + 8 * s, 0);
             }
         }
-    } else if (warp == 9 || warp == 10) {
+    } else if (warp > kEpi) {
         // ===== leader CTA: two MMA issuers, one thread each, for the pair =====
         // One stage costs the issuing thread ~600 cycles of serial latency (two mbarrier waits,
         // three tcgen05.mma, two commits) against ~520 cycles of tensor-pipe time, so the stages
-        // alternate between two threads: warp 9 owns the even ones (TMEM buffer 0), warp 10 the odd
+        // alternate between two threads: the first issuer warp owns the even ones (TMEM buffer 0), the second the odd
         // ones (buffer 1).  The buffers and shared-memory stages are disjoint and a commit covers
         // its own thread's MMAs, so the two instruction streams need no ordering between them.
         if (lane == 0) {
             mbar_wait(bar_a, 0);
             const uint32_t a_hi = smem_u32(smem + kOffA), a_lo = a_hi + kPartBytes;
             const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_lo);
-            const int buf = warp - 9;
+            const int buf = warp - (kEpi + 1);
             const uint32_t d = tmem_base + (uint32_t)(buf * kDStage);
-            for (int t = buf; t < n_stages; t += 2) {
+            for (int t = buf; t < n_visit; t += 2) {
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 const uint32_t tph = (uint32_t)((t >> 1) & 1);
-                if (!(dbg & 8)) mbar_wait(bar_tempty + 8 * buf, tph ^ 1);    // dbg 8: free-running MMA (profiling)
-                mbar_wait(bar_full + 8 * s, ph);
-                tc_fence_after();
                 const uint32_t b_hi = smem_u32(smem + kOffB + s * kTileBytes), b_lo = b_hi + kPartBytes;
                 const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_lo);
+                mbar_wait(bar_full + 8 * s, ph);                               // landed long ago, as a rule
+                FWAV_TRACE(0, t);
+                if (!(dbg & 8)) mbar_wait(bar_tempty + 8 * buf, tph ^ 1);    // dbg 8: free-running MMA (profiling)
+                FWAV_TRACE(1, t);
+                tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
-                umma_f16_pair(d, da_hi, db_lo, 0);
-                umma_f16_pair(d, da_lo, db_hi, 1);
-                umma_f16_pair(d, da_hi, db_hi, 1);
-                umma_commit_pair(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
+                if (!(dbg & 128)) {                         // dbg 128: one instruction per stage (timing experiment)
+                    umma_f16_pair(d, da_hi, db_lo, 0);
+                    umma_f16_pair(d, da_lo, db_hi, 1);
+                }
+                umma_f16_pair(d, da_hi, db_hi, (dbg & 128) ? 0 : 1);
                 umma_commit_pair(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
+                umma_commit_pair(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
+                FWAV_TRACE(2, t);
             }
             if (dbg & 8) {   // free-running profiling mode: drain the tensor pipe before leaving
                 umma_commit_pair(bar_a + 8 + 8 * buf);
                 mbar_wait(bar_a + 8 + 8 * buf, 0);
             }
         }
-    } else if (warp < 8) {
-        // ===== epilogue: one query row per thread, 128 of the stage's 256 columns per warp =====
-        const int quad = warp & 3, half = warp >> 2;
+    } else if (warp < kEpi) {
+        // ===== epilogue: one query row per thread; a warp owns 32 rows x (256 / (kEpi / 4)) columns of every stage =====
+        const int quad = warp & 3, half = warp >> 2;      // half: which column group (2 of 128 or 4 of 64)
         const int row0 = quad * 32;                       // first row of this warp inside the CTA tile
         const long long q = q_base + row0 + lane;
-        float tau = (q < n_q && (!active || active[q]) && !(dbg & 4)) ? -INFINITY : INFINITY;   // +inf: never a candidate
+        const bool live = q < n_q && (!active || active[q]) && !(dbg & 4);
+        constexpr int kCols = kDStage / (kEpi / 4);       // columns per warp and stage
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
+        // mode state
+        float tau = live ? -INFINITY : INFINITY;                    // LISTS: running threshold; +inf: never a candidate
         unsigned long long *lists = rows + ((size_t)row0 * 2 + half) * kCap;     // row r of the warp: lists + r * 2 * kCap
         uint32_t *scratch = reinterpret_cast<uint32_t *>(smem + kOffScratch) + warp * 128;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128);
-        int tt = t_first;
-        for (int t = 0; t < ((dbg & 8) ? 0 : n_stages); ++t) {
-            const int buf = t & 1;
-            const uint32_t tph = (uint32_t)((t >> 1) & 1);
-            mbar_wait(bar_tfull + 8 * buf, tph);
-            tc_fence_after();
-            const uint32_t ta = t_lane + (uint32_t)(buf * kDStage);
-            uint32_t v[kChunks][32];
-            unsigned hits = 0;
-            if (!(dbg & 2)) {
-                tmem_ld32(ta, v[0]);
-                tmem_ld32(ta + 32, v[1]);
-                tmem_wait_ld2(v[0], v[1]);
-                tmem_ld32(ta + 64, v[2]);        // in flight while the first two chunks are reduced
-                tmem_ld32(ta + 96, v[3]);
-                hits = (chunk_max(v[0]) > tau ? 1u : 0u) | (chunk_max(v[1]) > tau ? 2u : 0u);
-                tmem_wait_ld2(v[2], v[3]);
-            }
-            // the whole stage sits in registers: hand the TMEM buffer back before looking at the rest
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
-            const long long base = (long long)tt * kDStage + half * 128;
-            if (++tt == n_stages) tt = 0;
-            if (dbg & 3) continue;
-            hits |= (chunk_max(v[2]) > tau ? 4u : 0u) | (chunk_max(v[3]) > tau ? 8u : 0u);
-            if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
+        float t8[kThetaPart];                                       // THETA: largest scores of this column group, descending
+#pragma unroll
+        for (int i = 0; i < kThetaPart; ++i) t8[i] = live ? -INFINITY : INFINITY;
+        int cnt = 0;                                                // COLLECT
+        int32_t *cbuf = nullptr;
+        if (MODE == MODE_COLLECT) {
+            tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;  // +inf for pruned rows (written by pass 1)
+            cbuf = a.cbuf + ((q < n_q ? q : 0) * 4 + half) * (long long)a.cap;
         }
-        // both warps of a quadrant are done with their lists before the rows are finalised
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // ---- exact float32 re-score of the 2 x kKeep kept candidates of a row and best-first write-out ----
-        constexpr int kPerLane = 2 * kKeep / 32;
-        static_assert(2 * kKeep % 32 == 0, "final merge handles whole warps of keys");
-        for (int r = half * 16; r < half * 16 + 16; ++r) {
-            const long long qq = q_base + row0 + r;
-            if (qq >= n_q) break;
-            unsigned long long *keys = rows + (size_t)(row0 + r) * 2 * kCap;      // both column halves, contiguous
-            const float *qv = Q + qq * ED;
-            // canonical score (ascending-k float32 FMA chain) of every kept candidate
-            unsigned long long k[kPerLane];
-#pragma unroll
-            for (int i = 0; i < kPerLane; ++i) {
-                k[i] = keys[lane + 32 * i];
-                if ((uint32_t)(k[i] >> 32) != kNegInfBits) {
-                    const int id = (int)(0xFFFFFFFFu - (uint32_t)k[i]);
-                    k[i] = make_key(fwm::score_chain(qv, E + (long long)id * ED, ED), id);
+        int tt = t_first;
+        if (MODE == MODE_LISTS) {
+            for (int t = 0; t < ((dbg & 8) ? 0 : n_visit); ++t) {
+                const int buf = t & 1;
+                const uint32_t tph = (uint32_t)((t >> 1) & 1);
+                mbar_wait(bar_tfull + 8 * buf, tph);
+                tc_fence_after();
+                const uint32_t ta = t_lane + (uint32_t)(buf * kDStage);
+                uint32_t v[kChunks][32];
+                float m0 = -INFINITY, m1 = -INFINITY;
+                if (!(dbg & 2)) {
+                    tmem_ld32(ta, v[0]);
+                    tmem_ld32(ta + 32, v[1]);
+                    tmem_wait_ld2(v[0], v[1]);
+                    tmem_ld32(ta + 64, v[2]);        // in flight while the first two chunks are reduced
+                    tmem_ld32(ta + 96, v[3]);
+                    m0 = chunk_max(v[0]);
+                    m1 = chunk_max(v[1]);
+                    tmem_wait_ld2(v[2], v[3]);
+                }
+                // the whole stage sits in registers: hand the TMEM buffer back before looking at the rest
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0 && !((dbg & 32) && cta_rank)) mbar_arrive_remote(bar_tempty + 8 * buf, 0);   // dbg 32: timing experiment
+                const long long base = (long long)tt * kDStage + half * 128;
+                if (++tt == s_hi) tt = s_lo;
+                if (dbg & 3) continue;
+                const float m2 = chunk_max(v[2]), m3 = chunk_max(v[3]);
+                const unsigned hits = (m0 > tau ? 1u : 0u) | (m1 > tau ? 2u : 0u) | (m2 > tau ? 4u : 0u) | (m3 > tau ? 8u : 0u);
+                if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
+            }
+        } else if (!(dbg & 8)) {
+            // Streaming epilogue: 64 columns per warp and stage, four warps per scheduler interleave their chains.
+            for (int t = 0; t < n_visit; ++t) {
+                const int buf = t & 1;
+                mbar_wait(bar_tfull + 8 * buf, (uint32_t)((t >> 1) & 1));
+                tc_fence_after();
+                const uint32_t ta = t_lane + (uint32_t)(buf * kDStage);
+                uint32_t x0[32], x1[32];
+                tmem_ld32(ta, x0);
+                tmem_ld32(ta + 32, x1);
+                tmem_wait_ld2(x0, x1);
+                // this warp's share of the buffer is in registers: hand it back before looking at it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+                if (warp == 0 && lane == 0) FWAV_TRACE(4, t);
+                const int col0 = tt * kDStage + half * kCols;
+                if (++tt == s_hi) tt = s_lo;
+                if (dbg & 3) continue;
+                const float ma = chunk_max(x0), mb = chunk_max(x1);
+                if (MODE == MODE_THETA) {
+                    // every sampled score that beats this column group's current kThetaPart-th best
+                    if (ma > t8[kThetaPart - 1])
+                        for_each_ge(x0, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                            const float x = __uint_as_float(x0[j]);
+                            if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
+                        });
+                    if (mb > t8[kThetaPart - 1])
+                        for_each_ge(x1, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                            const float x = __uint_as_float(x1[j]);
+                            if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
+                        });
                 } else {
-                    k[i] = (unsigned long long)kNegInfBits << 32 | (uint32_t)(2 * kCap - 1 - (lane + 32 * i));   // distinct empties
+                    if (ma >= tau)
+                        for_each_ge(x0, tau, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + j;
+                            ++cnt;
+                        });
+                    if (mb >= tau)
+                        for_each_ge(x1, tau, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + 32 + j;
+                            ++cnt;
+                        });
                 }
+                if (warp == 0 && lane == 0) FWAV_TRACE(6, t);
             }
-            __syncwarp();
+        }
+        if (MODE == MODE_COLLECT) {
+            if (q < n_q) a.ccount[4 * q + half] = cnt;
+        } else if (MODE == MODE_THETA) {
+            // theta of a row = kTheta-th largest sampled score over the four column groups.  A group keeps
+            // its own kThetaPart best, so if more than that many of the row's best sit in one group the
+            // merged value comes out lower than the true one: more candidates, never fewer.
+            float *th = reinterpret_cast<float *>(smem + kOffMode);
+            if (half != 0) {
 #pragma unroll
-            for (int i = 0; i < kPerLane; ++i) keys[lane + 32 * i] = k[i];
-            __syncwarp();
-            int rk[kPerLane];
-#pragma unroll
-            for (int i = 0; i < kPerLane; ++i) rk[i] = 0;
-            for (int o = 0; o < 2 * kKeep; ++o) {
-                const unsigned long long ko = keys[o];
-#pragma unroll
-                for (int i = 0; i < kPerLane; ++i) rk[i] += ko > k[i] ? 1 : 0;
+                for (int i = 0; i < kThetaPart; ++i) th[((row0 + lane) * 3 + half - 1) * kThetaPart + i] = t8[i];
             }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (half == 0 && q < n_q) {
+                float tm[kTheta];
 #pragma unroll
-            for (int i = 0; i < kPerLane; ++i) {
-                if (rk[i] < top_k) {
-                    const bool live = (uint32_t)(k[i] >> 32) != kNegInfBits;
-                    cand[qq * top_k + rk[i]] = live ? (int)(0xFFFFFFFFu - (uint32_t)k[i]) : -1;
-                    if (scores) scores[qq * top_k + rk[i]] = live ? unorder_bits((uint32_t)(k[i] >> 32)) : -INFINITY;
+                for (int i = 0; i < kTheta; ++i) tm[i] = i < kThetaPart ? t8[i] : (live ? -INFINITY : INFINITY);
+                for (int i = 0; i < 3 * kThetaPart; ++i) {
+                    const float x = th[(row0 + lane) * 3 * kThetaPart + i];
+                    if (x > tm[kTheta - 1]) insert_desc(tm, x);
                 }
+                a.theta[q] = tm[kTheta - 1];      // +inf for pruned rows, -inf if the sample was too small
             }
-            __syncwarp();
+        } else {
+            // both warps of a quadrant are done with their lists before the rows are finalised
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (a.n_split > 1) {
+                // partial result of this share of the table: the raw keys, merged by merge_parts_kernel
+                for (int r = half * 16; r < half * 16 + 16; ++r) {
+                    const long long qq = q_base + row0 + r;
+                    if (qq >= n_q) break;
+                    const unsigned long long *keys = rows + (size_t)(row0 + r) * 2 * kCap;
+                    unsigned long long *dst = a.parts + (qq * a.n_split + split) * (2 * kCap);
+                    for (int i = lane; i < 2 * kCap; i += 32) dst[i] = keys[i];
+                }
+            } else {
+            // ---- exact float32 re-score of the 2 x kKeep kept candidates of a row and best-first write-out ----
+            constexpr int kPerLane = 2 * kKeep / 32;
+            static_assert(2 * kKeep % 32 == 0, "final merge handles whole warps of keys");
+            for (int r = half * 16; r < half * 16 + 16; ++r) {
+                const long long qq = q_base + row0 + r;
+                if (qq >= n_q) break;
+                unsigned long long *keys = rows + (size_t)(row0 + r) * 2 * kCap;      // both column halves, contiguous
+                const float *qv = a.Q + qq * ED;
+                // canonical score (ascending-k float32 FMA chain) of every kept candidate
+                unsigned long long k[kPerLane];
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) {
+                    k[i] = keys[lane + 32 * i];
+                    if ((uint32_t)(k[i] >> 32) != kNegInfBits) {
+                        const int id = (int)(0xFFFFFFFFu - (uint32_t)k[i]);
+                        k[i] = make_key(fwm::score_chain(qv, a.E + (long long)id * ED, ED), id);
+                    } else {
+                        k[i] = (unsigned long long)kNegInfBits << 32 | (uint32_t)(2 * kCap - 1 - (lane + 32 * i));   // distinct empties
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) keys[lane + 32 * i] = k[i];
+                __syncwarp();
+                int rk[kPerLane];
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) rk[i] = 0;
+                for (int o = 0; o < 2 * kKeep; ++o) {
+                    const unsigned long long ko = keys[o];
+#pragma unroll
+                    for (int i = 0; i < kPerLane; ++i) rk[i] += ko > k[i] ? 1 : 0;
+                }
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) {
+                    if (rk[i] < top_k) {
+                        const bool has = (uint32_t)(k[i] >> 32) != kNegInfBits;
+                        a.cand[qq * top_k + rk[i]] = has ? (int)(0xFFFFFFFFu - (uint32_t)k[i]) : -1;
+                        if (a.scores) a.scores[qq * top_k + rk[i]] = has ? unorder_bits((uint32_t)(k[i] >> 32)) : -INFINITY;
+                    }
+                }
+                __syncwarp();
+            }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the other may still signal it
-    if (warp == 8) {
+    if (warp == kEpi) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Pass 3 of the fast path: one warp per query.  Every collected candidate is
+// re-scored with the canonical float32 chain, the best top_k are selected
+// best-first (score descending, index ascending) and the result is VERIFIED:
+// a domain outside the collected set has a tensor-core score below theta, hence
+// a canonical score below theta + kScoreSlack; if the top_k-th selected score
+// reaches theta + kScoreSlack nothing outside can belong to the top_k.  Queries
+// that fail (too few candidates, buffer overflow, boundary within the slack) go
+// on the list for the exact MODE_LISTS kernel.
+// ---------------------------------------------------------------------------
+constexpr float kScoreSlack = 4e-6f;   // bound on |tensor-core score - canonical float32 score| (measured max 3.9e-7)
+constexpr int kFinWarps = 4;
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(kFull, x, o);
+        x = y > x ? y : x;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(kFinWarps * 32)
+finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
+                const uint8_t *__restrict__ active, const float *__restrict__ theta, const int32_t *__restrict__ cbuf,
+                const int *__restrict__ ccount, int cap, int32_t *__restrict__ cand, float *__restrict__ scores,
+                int *__restrict__ fail_list, int *__restrict__ fail_count) {
+    extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][4 * cap]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * kFinWarps + warp;
+    if (q >= n_q) return;
+    if (active && !active[q]) {
+        for (int i = lane; i < top_k; i += 32) {
+            cand[q * top_k + i] = -1;
+            if (scores) scores[q * top_k + i] = -INFINITY;
+        }
+        return;
+    }
+    unsigned long long *keys = fin_keys + (size_t)warp * 4 * cap;
+    int cn[4], c = 0;
+    bool ok = true, overflow = false;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        cn[g] = ccount[4 * q + g];
+        ok = ok && cn[g] <= cap;
+        c += cn[g];
+    }
+    overflow = !ok;
+    int n_sel = 0;
+    float last = -INFINITY;
+    if (ok) {
+        const int32_t *b0 = cbuf + (q * 4) * (long long)cap;
+        const int e1 = cn[0], e2 = e1 + cn[1], e3 = e2 + cn[2];
+        float qv[ED];
+#pragma unroll
+        for (int k = 0; k < ED; k += 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(Q + q * ED + k));
+            qv[k] = f.x; qv[k + 1] = f.y; qv[k + 2] = f.z; qv[k + 3] = f.w;
+        }
+        for (int i = lane; i < c; i += 32) {
+            const int id = i < e1 ? b0[i] : i < e2 ? b0[cap + i - e1] : i < e3 ? b0[2 * cap + i - e2] : b0[3 * cap + i - e3];
+            unsigned long long key = 0ull;                 // below every real key: padded columns
+            if (id < n_d) {
+                float ev[ED];
+#pragma unroll
+                for (int k = 0; k < ED; k += 4) {
+                    const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
+                    ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
+                }
+                key = make_key(fwm::score_chain(qv, ev, ED), id);
+            }
+            keys[i] = key;
+        }
+        __syncwarp();
+        // top_k rounds of "largest key below the previous one"
+        unsigned long long prev = ~0ull;
+        const int want = (long long)top_k < n_d ? top_k : (int)n_d;
+        for (int r = 0; r < want; ++r) {
+            unsigned long long best = 0ull;
+            for (int i = lane; i < c; i += 32) {
+                const unsigned long long k = keys[i];
+                if (k < prev && k > best) best = k;
+            }
+            best = warp_max_u64(best);
+            if (best == 0ull) break;
+            if (lane == 0) {
+                cand[q * top_k + r] = (int)(0xFFFFFFFFu - (uint32_t)best);
+                if (scores) scores[q * top_k + r] = unorder_bits((uint32_t)(best >> 32));
+            }
+            prev = best;
+            last = unorder_bits((uint32_t)(best >> 32));
+            ++n_sel;
+        }
+        ok = n_sel == want && last >= theta[q] + kScoreSlack;
+        for (int i = want + lane; i < top_k; i += 32) {      // table smaller than top_k: pad like the reference
+            cand[q * top_k + i] = -1;
+            if (scores) scores[q * top_k + i] = -INFINITY;
+        }
+    }
+    if (!ok && lane == 0) {
+        fail_list[atomicAdd(fail_count, 1)] = (int)q;
+        atomicAdd(fail_count + (overflow ? 1 : n_sel < top_k ? 2 : 3), 1);      // diagnostics: why
+    }
+}
+
+// fallback plumbing: the failed queries as a dense table, and their results back in place
+__global__ void gather_rows_kernel(const float *__restrict__ Q, const int *__restrict__ list, int n, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (ED / 4)) return;
+    const int r = i / (ED / 4), k = i % (ED / 4);
+    reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(Q + (long long)list[r] * ED) + k);
+}
+__global__ void scatter_cand_kernel(const int32_t *__restrict__ src, const float *__restrict__ src_scores,
+                                    const int *__restrict__ list, int n, int top_k, int32_t *__restrict__ cand,
+                                    float *__restrict__ scores) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * top_k) return;
+    const long long dst = (long long)list[i / top_k] * top_k + i % top_k;
+    cand[dst] = src[i];
+    if (scores) scores[dst] = src_scores[i];
+}
+
+// MODE_LISTS with n_split > 1: one warp per query merges the partial lists (n_split x 2 * kCap keys):
+// exact re-score of every kept candidate in place, then top_k rounds of "largest key below the previous one".
+__global__ void __launch_bounds__(128)
+merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, int n_split, int top_k,
+                   const uint8_t *__restrict__ active, unsigned long long *__restrict__ parts, int32_t *__restrict__ cand,
+                   float *__restrict__ scores) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 4 + warp;
+    if (q >= n_q) return;
+    if (active && !active[q]) {
+        for (int i = lane; i < top_k; i += 32) {
+            cand[q * top_k + i] = -1;
+            if (scores) scores[q * top_k + i] = -INFINITY;
+        }
+        return;
+    }
+    unsigned long long *keys = parts + q * n_split * (2 * kCap);
+    const int c = n_split * 2 * kCap;
+    const float *qv = Q + q * ED;
+    for (int i = lane; i < c; i += 32) {
+        unsigned long long k = keys[i];
+        if ((uint32_t)(k >> 32) != kNegInfBits) {
+            const int id = (int)(0xFFFFFFFFu - (uint32_t)k);
+            k = make_key(fwm::score_chain(qv, E + (long long)id * ED, ED), id);
+        } else {
+            k = 0ull;
+        }
+        keys[i] = k;
+    }
+    __syncwarp();
+    unsigned long long prev = ~0ull;
+    int r = 0;
+    for (; r < top_k; ++r) {
+        unsigned long long best = 0ull;
+        for (int i = lane; i < c; i += 32) {
+            const unsigned long long k = keys[i];
+            if (k < prev && k > best) best = k;
+        }
+        best = warp_max_u64(best);
+        if (best == 0ull) break;
+        if (lane == 0) {
+            cand[q * top_k + r] = (int)(0xFFFFFFFFu - (uint32_t)best);
+            if (scores) scores[q * top_k + r] = unorder_bits((uint32_t)(best >> 32));
+        }
+        prev = best;
+    }
+    for (int i = r + lane; i < top_k; i += 32) {
+        cand[q * top_k + i] = -1;
+        if (scores) scores[q * top_k + i] = -INFINITY;
     }
 }
 
@@ -541,6 +949,60 @@ topk_umma_kernel(const uint4 *__restrict__ q_tiles, const uint4 *__restrict__ e_
 bool fwav_topk_umma_supported(int emb_dim, int top_k, int64_t n_q, int64_t n_d) {
     return emb_dim == ED && top_k >= 1 && top_k <= 32 && n_q > 0 && n_d > 0;
 }
+
+namespace {
+
+constexpr int kCollectCap = 192;              // candidate indices kept per (query, column group of 64)
+constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
+constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
+constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
+
+inline int grid_for(const fwav_ctx *ctx, long long work) {
+    long long need = (work + 255) / 256, cap = (long long)ctx->num_sms * 8;
+    return (int)(need < cap ? need : cap);
+}
+
+int set_smem_attrs(fwav_ctx *ctx) {
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLists));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_THETA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTheta));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
+    return FWAV_OK;
+}
+
+// exact list kernel over packed tiles (small tables, forced mode, fallback of the fast path)
+int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const float *d_q, const float *d_emb, long long n_q,
+                 long long n_d, int n_stages, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores, int dbg,
+                 cudaStream_t st) {
+    ScanArgs a = {};
+    a.q_tiles = d_qt; a.e_tiles = d_et; a.Q = d_q; a.E = d_emb; a.n_q = n_q; a.n_d = n_d;
+    a.n_stages = n_stages; a.top_k = top_k; a.active = d_active; a.cand = d_cand; a.scores = d_scores;
+    a.dbg = dbg;
+    const long long q_pairs = (n_q + kQPair - 1) / kQPair;
+    // few queries: split the table between several CTA pairs per 256 queries so that the machine is full
+    const long long resident = ctx->num_sms / 2;
+    long long split = 1;
+    if (q_pairs < resident && !dbg) {
+        split = resident / q_pairs;
+        if (split > 64) split = 64;
+        if (split > n_stages / 8) split = n_stages / 8;
+        if (split < 1) split = 1;
+    }
+    a.n_split = (int)split;
+    if (split > 1) {
+        int rc;
+        if ((rc = fwav_ws_reserve(ctx, WS_UMMA_PARTS, (size_t)n_q * split * 2 * kCap * 8, (void **)&a.parts))) return rc;
+    }
+    scan_kernel<MODE_LISTS><<<(unsigned)(2 * q_pairs * split), n_threads(MODE_LISTS), kSmemLists, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
+    if (split > 1) {
+        merge_parts_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_q, d_emb, n_q, (int)split, top_k, d_active, a.parts,
+                                                                    d_cand, d_scores);
+        FWAV_LAUNCH_CHECK(ctx);
+    }
+    return FWAV_OK;
+}
+
+}  // namespace
 
 int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const float *d_emb, int64_t n_d,
                           int emb_dim, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores,
@@ -559,19 +1021,112 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     int rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_E, (size_t)e_tiles * kTileBytes, (void **)&d_et))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_Q, (size_t)q_tiles * kTileBytes, (void **)&d_qt))) return rc;
-    auto grid_for = [&](long long work) {
-        long long need = (work + 255) / 256, cap = (long long)ctx->num_sms * 8;
-        return (int)(need < cap ? need : cap);
-    };
-    pack_f16_tiles_kernel<<<grid_for(e_tiles * kDTile * 2), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et);
+    pack_f16_tiles_kernel<<<grid_for(ctx, e_tiles * kDTile * 2), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et, 1);
     FWAV_LAUNCH_CHECK(ctx);
-    pack_f16_tiles_kernel<<<grid_for(q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt);
+    pack_f16_tiles_kernel<<<grid_for(ctx, q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt, 1);
     FWAV_LAUNCH_CHECK(ctx);
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if ((rc = set_smem_attrs(ctx))) return rc;
     const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
-    topk_umma_kernel<<<(unsigned)(2 * q_pairs), kThreads, kSmemBytes, st>>>(d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages,
-                                                                           top_k, d_active, d_cand, d_scores, dbg);
+    const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
+    const bool fast = n_d >= kFastMinDomains && !(mode_env && !strcmp(mode_env, "lists"));
+    if (!fast)
+        return launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st);
+
+    // ---- fast path: sampled threshold, collect, finalize + verify, exact fallback for the failures ----
+    // pass 1 scans a strided sample of the table (every 16th domain), packed like the table itself:
+    // neighbouring domains are near-duplicates of each other, a strided sample is not
+    const long long n_samp = (n_d + kSampleStride - 1) / kSampleStride;
+    const long long s_stages = (n_samp + kDStage - 1) / kDStage;
+    uint4 *d_es = nullptr;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_MISC, (size_t)s_stages * 2 * kTileBytes, (void **)&d_es))) return rc;
+    pack_f16_tiles_kernel<<<grid_for(ctx, s_stages * 2 * kDTile * 2), 256, 0, st>>>(d_emb, n_d, s_stages * 2, d_es, kSampleStride);
     FWAV_LAUNCH_CHECK(ctx);
+    const long long batch = n_q < kBatchQueries ? n_q : kBatchQueries;
+    float *d_theta = nullptr;
+    int32_t *d_cbuf = nullptr;
+    int *d_cnt = nullptr, *d_fail = nullptr;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)n_q * sizeof(float), (void **)&d_theta))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * kCollectCap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
+    int *d_fail_count = d_fail + n_q;
+    FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
+    for (long long q0 = 0; q0 < n_q; q0 += batch) {
+        const long long nq = n_q - q0 < batch ? n_q - q0 : batch;      // batch is a multiple of kQPair unless it is everything
+        const long long pairs = (nq + kQPair - 1) / kQPair;
+        ScanArgs a = {};
+        a.q_tiles = d_qt + (q0 / kQTile) * (kTileBytes / 16);
+        a.e_tiles = d_et; a.Q = d_q + q0 * ED; a.E = d_emb; a.n_q = nq; a.n_d = n_d;
+        a.n_stages = (int)n_stages; a.top_k = top_k; a.active = d_active ? d_active + q0 : nullptr;
+        a.theta = d_theta + q0; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = kCollectCap; a.dbg = dbg;
+        a.n_split = 1;
+        a.e_tiles = d_es; a.n_stages = (int)s_stages;
+        scan_kernel<MODE_THETA><<<(unsigned)(2 * pairs), n_threads(MODE_THETA), kSmemTheta, st>>>(a);
+        FWAV_LAUNCH_CHECK(ctx);
+        a.e_tiles = d_et; a.n_stages = (int)n_stages;
+        if (dbg & 64) {
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, kTraceStages * 8 * sizeof(long long), (void **)&a.trace))) return rc;
+            FWAV_CUDA(ctx, cudaMemsetAsync(a.trace, 0, kTraceStages * 8 * sizeof(long long), st));
+        }
+        scan_kernel<MODE_COLLECT><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
+        FWAV_LAUNCH_CHECK(ctx);
+        if (dbg & 64) {
+            static long long h_trace[kTraceStages * 8];
+            FWAV_CUDA(ctx, cudaMemcpyAsync(h_trace, a.trace, sizeof h_trace, cudaMemcpyDeviceToHost, st));
+            FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+            FILE *f = fopen("gpurun_out/umma_trace.txt", "w");
+            if (f) {
+                fprintf(f, "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
+                const long long t0 = h_trace[0];
+                for (int i = 0; i < kTraceStages; ++i) {
+                    fprintf(f, "%4d:", kTraceFrom + i);
+                    for (int k = 0; k < 8; ++k) fprintf(f, " %8lld", h_trace[i * 8 + k] ? h_trace[i * 8 + k] - t0 : -1ll);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+        finalize_kernel<<<(unsigned)((nq + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
+                          (size_t)kFinWarps * 4 * kCollectCap * sizeof(unsigned long long), st>>>(
+            d_q + q0 * ED, d_emb, nq, n_d, top_k, d_active ? d_active + q0 : nullptr, d_theta + q0, d_cbuf, d_cnt,
+            kCollectCap, d_cand + q0 * top_k, d_scores ? d_scores + q0 * top_k : nullptr, d_fail, d_fail_count);
+        FWAV_LAUNCH_CHECK(ctx);
+        // NOTE: fail_list holds batch-local indices; resolve this batch's failures before the next one
+        int h_fail[4] = {0, 0, 0, 0};
+        FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail, d_fail_count, sizeof h_fail, cudaMemcpyDeviceToHost, st));
+        FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+        const int n_fail = h_fail[0];
+        ctx->umma_fallback_queries += n_fail;
+        if (getenv("FWAV_UMMA_VERBOSE"))
+            fprintf(stderr, "[fwav] search batch at %lld: %d of %lld queries to the exact list kernel (overflow %d, short %d, boundary %d)\n",
+                    q0, n_fail, nq, h_fail[1], h_fail[2], h_fail[3]);
+        if (n_fail > 0 && dbg) FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));   // profiling modes: wrong anyway
+        if (n_fail > 0 && !dbg) {
+            const long long fp = (n_fail + kQPair - 1) / kQPair;
+            float *d_fq = nullptr, *d_fs = nullptr;
+            uint4 *d_fqt = nullptr;
+            int32_t *d_fc = nullptr;
+            unsigned char *blk = nullptr;
+            const size_t sz_q = (size_t)fp * kQPair * ED * sizeof(float), sz_t = (size_t)fp * 2 * kTileBytes,
+                         sz_c = (size_t)n_fail * top_k * sizeof(int32_t);
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, sz_q + sz_t + 2 * sz_c + 64, (void **)&blk))) return rc;
+            d_fq = reinterpret_cast<float *>(blk);
+            d_fqt = reinterpret_cast<uint4 *>(blk + sz_q);
+            d_fc = reinterpret_cast<int32_t *>(blk + sz_q + sz_t);
+            d_fs = reinterpret_cast<float *>(blk + sz_q + sz_t + sz_c);
+            gather_rows_kernel<<<(n_fail * (ED / 4) + 255) / 256, 256, 0, st>>>(d_q + q0 * ED, d_fail, n_fail, d_fq);
+            FWAV_LAUNCH_CHECK(ctx);
+            pack_f16_tiles_kernel<<<grid_for(ctx, fp * 2 * kDTile * 2), 256, 0, st>>>(d_fq, n_fail, fp * 2, d_fqt, 1);
+            FWAV_LAUNCH_CHECK(ctx);
+            if ((rc = launch_lists(ctx, d_fqt, d_et, d_fq, d_emb, n_fail, n_d, (int)n_stages, top_k, nullptr, d_fc, d_fs, dbg, st)))
+                return rc;
+            scatter_cand_kernel<<<(n_fail * top_k + 255) / 256, 256, 0, st>>>(d_fc, d_fs, d_fail, n_fail, top_k,
+                                                                               d_cand + q0 * top_k,
+                                                                               d_scores ? d_scores + q0 * top_k : nullptr);
+            FWAV_LAUNCH_CHECK(ctx);
+            FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
+        }
+    }
     return FWAV_OK;
 }

@@ -38,6 +38,7 @@ SIGNATURES = [
     ("fwav_ctx_sync", C.c_int, [c_ctx]),
     ("fwav_ctx_set_search_impl", C.c_int, [c_ctx, C.c_int]),
     ("fwav_ctx_launch_count", i64, [c_ctx]),
+    ("fwav_ctx_search_fallbacks", i64, [c_ctx]),
     ("fwav_geometry", C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("fwav_count_domains", i64, [i64, C.c_int, C.c_int]),
     ("fwav_build_domains", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
@@ -189,6 +190,9 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.fwav_ctx_launch_count(self.h))
+
+    def search_fallbacks(self):
+        return int(self.lib.fwav_ctx_search_fallbacks(self.h))
 
     def upload(self, arr):
         return DeviceBuffer.from_host(self, arr)

@@ -60,6 +60,9 @@ int fwav_ctx_sync(fwav_ctx *ctx);
 int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl);
 /* Number of kernels this library has launched through `ctx` since creation. */
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx);
+/* Queries the tensor-core search handed from its sampled-threshold fast path to the exact list kernel since
+   creation (verification failed or candidate buffer overflowed).  Diagnostics only; results are exact either way. */
+int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx);
 
 /* Derived geometry of compress_audio (fractal.py:1070-1071) and the domain
  * count of build_domains_memmap (fractal.py:297-304). */

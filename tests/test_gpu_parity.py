@@ -375,6 +375,50 @@ def test_large_search_properties(ctx):
         assert np.array_equal(results["umma"], got)
 
 
+def test_search_paths_agree(ctx, monkeypatch):
+    """The tensor-core search has three routes (sampled-threshold fast path, exact list kernel, list
+    kernel split over the table for few queries).  On one table, with a pruning mask, every route has
+    to return the FFMA kernel's candidates and canonical float32 scores, best-first."""
+    from fwav_b200 import _lib, synth
+    sig = synth.music_like(seconds=12.0, rate=44100, seed=5)
+    tile, N, ds, K, ED = 4096, 16, 4, 32, 16
+    n_d = _lib.count_domains(len(sig), tile, ds)
+    assert n_d >= 1 << 16            # large enough for the fast path
+    d_sig = ctx.upload(sig)
+    d_dom = ctx.alloc(n_d * N * 4)
+    d_emb = ctx.alloc(n_d * ED * 4)
+    ctx.build_domains(d_sig.ptr, len(sig), tile, N, ds, d_dom.ptr)
+    ctx.embed(d_dom.ptr, n_d, N, ED, d_emb.ptr)
+    rng = np.random.default_rng(3)
+
+    def run(impl, n_q, mask, mode=None):
+        if mode:
+            monkeypatch.setenv("FWAV_UMMA_MODE", mode)
+        else:
+            monkeypatch.delenv("FWAV_UMMA_MODE", raising=False)
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * K * 4), ctx.alloc(n_q * K * 4)
+        d_act = ctx.upload(mask.astype(np.uint8))
+        try:
+            ctx.topk(d_emb.ptr, n_q, d_emb.ptr, n_d, ED, K, d_act.ptr, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        return d_cand.to_host((n_q, K), np.int32), d_sc.to_host((n_q, K), np.float32)
+
+    for n_q in (5000, 300):          # 300 queries: two CTA pairs, so the list kernel splits the table
+        mask = rng.random(n_q) > 0.2
+        mask[256:512] = False        # a whole CTA pair pruned
+        want, want_sc = run("ffma", n_q, mask)
+        assert (want[~mask] == -1).all() and (want[mask] >= 0).all()
+        for mode in (None, "lists"):
+            before = ctx.search_fallbacks()
+            got, got_sc = run("umma", n_q, mask, mode)
+            assert np.array_equal(got, want), (n_q, mode, np.flatnonzero((got != want).any(axis=1))[:10])
+            assert np.array_equal(bits(got_sc[mask]), bits(want_sc[mask])), (n_q, mode)
+            print(f"n_q={n_q} mode={mode or 'fast'}: equal to FFMA; "
+                  f"{ctx.search_fallbacks() - before} queries went to the exact list kernel")
+
+
 def test_decode_properties(ctx):
     """Full-size-style checks that need no oracle: stored-s one-shot limit, idempotence."""
     rng = np.random.default_rng(1)
