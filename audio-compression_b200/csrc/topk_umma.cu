@@ -568,11 +568,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 FWAV_TRACE(1, t);
                 tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
-                if (!(dbg & 128)) {                         // dbg 128: one instruction per stage (timing experiment)
-                    umma_f16_pair(d, da_hi, db_lo, 0);
-                    umma_f16_pair(d, da_lo, db_hi, 1);
-                }
-                umma_f16_pair(d, da_hi, db_hi, (dbg & 128) ? 0 : 1);
+                umma_f16_pair(d, da_hi, db_lo, 0);
+                umma_f16_pair(d, da_lo, db_hi, 1);
+                umma_f16_pair(d, da_hi, db_hi, 1);
                 umma_commit_pair(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
                 umma_commit_pair(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
                 FWAV_TRACE(2, t);
