@@ -85,6 +85,9 @@ int fwav_ctx_destroy(fwav_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < WS_COUNT; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    for (auto &slot : ctx->search_ev)
+        for (cudaEvent_t e : slot)
+            if (e) cudaEventDestroy(e);
     if (ctx->d_tonal) cudaFree(ctx->d_tonal);
     if (ctx->d_transient) cudaFree(ctx->d_transient);
     if (ctx->d_w) cudaFree(ctx->d_w);
@@ -112,6 +115,18 @@ int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl) {
 
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx) { return ctx ? ctx->umma_fallback_queries : 0; }
+int fwav_ctx_search_timings(fwav_ctx *ctx, float ms[5]) {
+    if (!ctx || !ms) return FWAV_ERR_INVALID;
+    FWAV_REQUIRE(ctx, ctx->search_slots_used > 0, "no tensor-core search has run on this context yet");
+    for (int k = 0; k < fwav_ctx::kSearchPhases; ++k) ms[k] = 0.0f;
+    for (int b = 0; b < ctx->search_slots_used; ++b)
+        for (int k = 0; k < fwav_ctx::kSearchPhases; ++k) {
+            float t = 0.0f;
+            FWAV_CUDA(ctx, cudaEventElapsedTime(&t, ctx->search_ev[b][k], ctx->search_ev[b][k + 1]));
+            ms[k] += t;
+        }
+    return FWAV_OK;
+}
 
 int fwav_geometry(int tile_size, int *range_size, int *domain_step) {
     const int rs = tile_size / 256 > 4 ? tile_size / 256 : 4;      // fractal.py:1070

@@ -19,6 +19,12 @@ struct fwav_ctx {
     int search_impl = FWAV_SEARCH_AUTO;
     int64_t launches = 0;
     int64_t umma_fallback_queries = 0;   // queries the fast search path handed to the exact list kernel
+    // CUDA events around the kernels of the last tensor-core search call (fwav_ctx_search_timings)
+    static constexpr int kSearchPhases = 5;          // pack, threshold pass, collect pass, finalize, list kernel
+    static constexpr int kSearchSlots = 8;           // batches per call that are timed
+    cudaEvent_t search_ev[kSearchSlots][kSearchPhases + 1] = {};
+    int search_slots_used = 0;
+    bool search_fast_path = false;
 
     // embedding matrices cached per (N, half)
     int emb_N = 0, emb_half = 0;

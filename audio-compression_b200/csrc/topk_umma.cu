@@ -967,6 +967,14 @@ int set_smem_attrs(fwav_ctx *ctx) {
     return FWAV_OK;
 }
 
+// record phase boundary k of timed batch `slot` (events are created on first use)
+int mark(fwav_ctx *ctx, int slot, int k, cudaStream_t st) {
+    if (slot >= fwav_ctx::kSearchSlots) return FWAV_OK;
+    if (!ctx->search_ev[slot][k]) FWAV_CUDA(ctx, cudaEventCreate(&ctx->search_ev[slot][k]));
+    FWAV_CUDA(ctx, cudaEventRecord(ctx->search_ev[slot][k], st));
+    return FWAV_OK;
+}
+
 // exact list kernel over packed tiles (small tables, forced mode, fallback of the fast path)
 int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const float *d_q, const float *d_emb, long long n_q,
                  long long n_d, int n_stages, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores, int dbg,
@@ -1019,6 +1027,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     int rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_E, (size_t)e_tiles * kTileBytes, (void **)&d_et))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_Q, (size_t)q_tiles * kTileBytes, (void **)&d_qt))) return rc;
+    ctx->search_slots_used = 0;
+    if ((rc = mark(ctx, 0, 0, st))) return rc;
     pack_f16_tiles_kernel<<<grid_for(ctx, e_tiles * kDTile * 2), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et, 1);
     FWAV_LAUNCH_CHECK(ctx);
     pack_f16_tiles_kernel<<<grid_for(ctx, q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt, 1);
@@ -1028,8 +1038,16 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
     const bool fast = n_d >= kFastMinDomains && !(mode_env && !strcmp(mode_env, "lists"));
-    if (!fast)
-        return launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st);
+    ctx->search_fast_path = fast;
+    if (!fast) {
+        for (int k = 1; k <= 4; ++k)
+            if ((rc = mark(ctx, 0, k, st))) return rc;
+        if ((rc = launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st)))
+            return rc;
+        if ((rc = mark(ctx, 0, 5, st))) return rc;
+        ctx->search_slots_used = 1;
+        return FWAV_OK;
+    }
 
     // ---- fast path: sampled threshold, collect, finalize + verify, exact fallback for the failures ----
     // pass 1 scans a strided sample of the table (every 16th domain), packed like the table itself:
@@ -1050,7 +1068,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
     int *d_fail_count = d_fail + n_q;
     FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
-    for (long long q0 = 0; q0 < n_q; q0 += batch) {
+    int slot = 0;
+    for (long long q0 = 0; q0 < n_q; q0 += batch, ++slot) {
+        if (slot > 0 && (rc = mark(ctx, slot, 0, st))) return rc;      // later batches: nothing to pack
+        if ((rc = mark(ctx, slot, 1, st))) return rc;
         const long long nq = n_q - q0 < batch ? n_q - q0 : batch;      // batch is a multiple of kQPair unless it is everything
         const long long pairs = (nq + kQPair - 1) / kQPair;
         ScanArgs a = {};
@@ -1062,6 +1083,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
         scan_kernel<MODE_THETA><<<(unsigned)(2 * pairs), n_threads(MODE_THETA), kSmemTheta, st>>>(a);
         FWAV_LAUNCH_CHECK(ctx);
+        if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {
             if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, kTraceStages * 8 * sizeof(long long), (void **)&a.trace))) return rc;
@@ -1069,6 +1091,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         }
         scan_kernel<MODE_COLLECT><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
         FWAV_LAUNCH_CHECK(ctx);
+        if ((rc = mark(ctx, slot, 3, st))) return rc;
         if (dbg & 64) {
             static long long h_trace[kTraceStages * 8];
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_trace, a.trace, sizeof h_trace, cudaMemcpyDeviceToHost, st));
@@ -1090,6 +1113,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             d_q + q0 * ED, d_emb, nq, n_d, top_k, d_active ? d_active + q0 : nullptr, d_theta + q0, d_cbuf, d_cnt,
             kCollectCap, d_cand + q0 * top_k, d_scores ? d_scores + q0 * top_k : nullptr, d_fail, d_fail_count);
         FWAV_LAUNCH_CHECK(ctx);
+        if ((rc = mark(ctx, slot, 4, st))) return rc;
         // NOTE: fail_list holds batch-local indices; resolve this batch's failures before the next one
         int h_fail[4] = {0, 0, 0, 0};
         FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail, d_fail_count, sizeof h_fail, cudaMemcpyDeviceToHost, st));
@@ -1125,6 +1149,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             FWAV_LAUNCH_CHECK(ctx);
             FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
         }
+        if ((rc = mark(ctx, slot, 5, st))) return rc;
+        if (slot < fwav_ctx::kSearchSlots) ctx->search_slots_used = slot + 1;
     }
     return FWAV_OK;
 }

@@ -39,6 +39,7 @@ SIGNATURES = [
     ("fwav_ctx_set_search_impl", C.c_int, [c_ctx, C.c_int]),
     ("fwav_ctx_launch_count", i64, [c_ctx]),
     ("fwav_ctx_search_fallbacks", i64, [c_ctx]),
+    ("fwav_ctx_search_timings", C.c_int, [c_ctx, C.POINTER(C.c_float)]),
     ("fwav_geometry", C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("fwav_count_domains", i64, [i64, C.c_int, C.c_int]),
     ("fwav_build_domains", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
@@ -193,6 +194,13 @@ class Context:
 
     def search_fallbacks(self):
         return int(self.lib.fwav_ctx_search_fallbacks(self.h))
+
+    def search_timings(self):
+        """Device milliseconds of the last tensor-core search: pack, threshold pass, collect pass,
+        finalize, exact list kernel (call after synchronising the stream)."""
+        ms = (C.c_float * 5)()
+        self._check(self.lib.fwav_ctx_search_timings(self.h, ms))
+        return dict(zip(("pack", "threshold", "collect", "finalize", "lists"), [float(x) for x in ms]))
 
     def upload(self, arr):
         return DeviceBuffer.from_host(self, arr)

@@ -63,6 +63,12 @@ int64_t fwav_ctx_launch_count(const fwav_ctx *ctx);
 /* Queries the tensor-core search handed from its sampled-threshold fast path to the exact list kernel since
    creation (verification failed or candidate buffer overflowed).  Diagnostics only; results are exact either way. */
 int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx);
+/* Device time, in milliseconds, of the phases of the LAST tensor-core fwav_topk / fwav_compress_* search on `ctx`,
+   from CUDA events recorded on its stream: ms[0] operand packing, ms[1] threshold pass (sample table), ms[2] collect
+   pass (the dominant kernel: every query against every domain), ms[3] finalize (exact re-score + verification),
+   ms[4] exact list kernel (small tables, or the queries the fast path handed over).  Call after the stream has been
+   synchronised; returns FWAV_ERR_INVALID if no tensor-core search has run yet. */
+int fwav_ctx_search_timings(fwav_ctx *ctx, float ms[5]);
 
 /* Derived geometry of compress_audio (fractal.py:1070-1071) and the domain
  * count of build_domains_memmap (fractal.py:297-304). */
