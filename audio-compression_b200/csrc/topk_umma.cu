@@ -149,6 +149,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > (1u << 22)) __trap();   // a lost arrival must fail loudly, never hang the GPU
     }
 }
+// hot-loop wait: no watchdog (the MMA threads and the producer keep theirs, so a lost arrival still traps)
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -215,6 +225,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 // wait for the loads; the registers are threaded through so no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld1(uint32_t (&a)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a)::"memory");
+}
 __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&a)[32], uint32_t (&b)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a), FWAV_RW32(b)::"memory");
 }
@@ -636,22 +649,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
             // Streaming epilogue: 64 columns per warp and stage, four warps per scheduler interleave their chains.
             for (int t = 0; t < n_visit; ++t) {
                 const int buf = t & 1;
-                mbar_wait(bar_tfull + 8 * buf, (uint32_t)((t >> 1) & 1));
+                mbar_wait_hot(bar_tfull + 8 * buf, (uint32_t)((t >> 1) & 1));
                 tc_fence_after();
                 const uint32_t ta = t_lane + (uint32_t)(buf * kDStage);
                 uint32_t x0[32], x1[32];
                 tmem_ld32(ta, x0);
-                tmem_ld32(ta + 32, x1);
-                tmem_wait_ld2(x0, x1);
-                // this warp's share of the buffer is in registers: hand it back before looking at it
+                tmem_wait_ld1(x0);
+                tmem_ld32(ta + 32, x1);          // in flight while the first chunk is reduced: the four warps of a
+                const float ma = chunk_max(x0);  // scheduler then interleave TMEM-port and ALU time instead of
+                tmem_wait_ld1(x1);               // all loading first and all reducing afterwards
+                // this warp's share of the buffer is in registers: hand it back before looking at the rest
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
-                if (warp == 0 && lane == 0) FWAV_TRACE(4, t);
                 const int col0 = tt * kDStage + half * kCols;
                 if (++tt == s_hi) tt = s_lo;
-                if (dbg & 3) continue;
-                const float ma = chunk_max(x0), mb = chunk_max(x1);
+                const float mb = chunk_max(x1);
                 if (MODE == MODE_THETA) {
                     // every sampled score that beats this column group's current kThetaPart-th best
                     if (ma > t8[kThetaPart - 1])
@@ -676,7 +689,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                             ++cnt;
                         });
                 }
-                if (warp == 0 && lane == 0) FWAV_TRACE(6, t);
             }
         }
         if (MODE == MODE_COLLECT) {
