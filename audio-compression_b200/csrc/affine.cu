@@ -33,7 +33,7 @@ __device__ __forceinline__ bool better(float e1, int p1, float e2, int p2) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NT == 16 ? 3 : 1)
 affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
               const float *__restrict__ domains, const int32_t *__restrict__ cand, int K, float clipf,
               int32_t *__restrict__ o_idx, float *__restrict__ o_s, float *__restrict__ o_o,

@@ -28,6 +28,64 @@ half_sums_kernel(const float *__restrict__ signal, long long n_half, int stride,
         half[i] = fwm::half_sum128(sig, i * stride);
 }
 
+// stride % 4 == 0 (domain_step a multiple of 4): every leaf starts on a 16-byte boundary, so the 128 samples are
+// 32 aligned float4 loads (a warp's load covers 512 contiguous bytes) instead of 128 scalar loads 16 bytes apart.
+// Same eight strided accumulators, same order of additions as npm::pairwise_leaf.
+__global__ void __launch_bounds__(256)
+half_sums_vec4_kernel(const float *__restrict__ signal, long long n_half, int stride,
+                      float *__restrict__ half) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_half;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 *p = reinterpret_cast<const float4 *>(signal + i * stride);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        float r0 = a.x, r1 = a.y, r2 = a.z, r3 = a.w, r4 = b.x, r5 = b.y, r6 = b.z, r7 = b.w;
+#pragma unroll
+        for (int m = 1; m < 16; ++m) {
+            a = __ldg(p + 2 * m);
+            b = __ldg(p + 2 * m + 1);
+            r0 = npm::add(r0, a.x); r1 = npm::add(r1, a.y); r2 = npm::add(r2, a.z); r3 = npm::add(r3, a.w);
+            r4 = npm::add(r4, b.x); r5 = npm::add(r5, b.y); r6 = npm::add(r6, b.z); r7 = npm::add(r7, b.w);
+        }
+        half[i] = npm::add(npm::add(npm::add(r0, r1), npm::add(r2, r3)), npm::add(npm::add(r4, r5), npm::add(r6, r7)));
+    }
+}
+
+// N == 16, run == 256: a block builds 256 consecutive domains per pass.  Column k of those rows needs the half
+// sums at (j*ds + k*256) / stride and + 128 / stride for 256 consecutive j: contiguous reads per k; the 256 x 16
+// tile is transposed through shared memory so that the rows leave as coalesced float4 stores (16 KB per block).
+constexpr int kTileJ = 256;
+__global__ void __launch_bounds__(256)
+domains_from_halves_t16_kernel(const float *__restrict__ half, long long n_dom, int ds, int stride,
+                               float *__restrict__ domains) {
+    __shared__ float tile[kTileJ][17];
+    const int step = ds / stride;                 // half-sum index advance per domain (stride divides ds)
+    const int kstep = 256 / stride, hstep = 128 / stride;
+    for (long long j0 = (long long)blockIdx.x * kTileJ; j0 < n_dom; j0 += (long long)gridDim.x * kTileJ) {
+        const long long j = j0 + threadIdx.x;
+        if (j < n_dom) {
+            float h0[16], h1[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {          // all 32 loads in flight before the first add
+                const long long h = j * step + (long long)k * kstep;
+                h0[k] = __ldg(half + h);
+                h1[k] = __ldg(half + h + hstep);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) tile[threadIdx.x][k] = fwm::domain_from_halves(h0[k], h1[k]);
+        }
+        __syncthreads();
+        // 256 rows x 16 floats = 1024 float4: thread t writes float4 t + 256 i (i = 0..3), 4 KB contiguous per i
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = threadIdx.x + 256 * i, jj = f >> 2, q = f & 3;
+            if (j0 + jj < n_dom)
+                st_stream_f4(reinterpret_cast<float4 *>(domains + (j0 + jj) * 16) + q,
+                             make_float4(tile[jj][4 * q], tile[jj][4 * q + 1], tile[jj][4 * q + 2], tile[jj][4 * q + 3]));
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 domains_from_halves_kernel(const float *__restrict__ half, long long n_out, int N, int ds,
                            int stride, float *__restrict__ domains) {
@@ -106,10 +164,18 @@ int fwav_launch_domains(fwav_ctx *ctx, const float *d_signal, int64_t n, int til
         float *d_half = nullptr;
         int rc = fwav_ws_reserve(ctx, WS_HALF, sizeof(float) * (size_t)n_half, (void **)&d_half);
         if (rc) return rc;
-        half_sums_kernel<<<grid_for(n_half, 256, ctx->num_sms, 8), 256, 0, st>>>(d_signal, n_half, stride, d_half);
+        const bool sig16 = (reinterpret_cast<uintptr_t>(d_signal) & 15) == 0;
+        if (stride % 4 == 0 && sig16)
+            half_sums_vec4_kernel<<<grid_for(n_half, 256, ctx->num_sms, 8), 256, 0, st>>>(d_signal, n_half, stride, d_half);
+        else
+            half_sums_kernel<<<grid_for(n_half, 256, ctx->num_sms, 8), 256, 0, st>>>(d_signal, n_half, stride, d_half);
         FWAV_LAUNCH_CHECK(ctx);
-        domains_from_halves_kernel<<<grid_for(n_out, 256, ctx->num_sms, 8), 256, 0, st>>>(
-            d_half, n_out, N, ds, stride, d_domains);
+        if (N == 16 && (reinterpret_cast<uintptr_t>(d_domains) & 15) == 0)
+            domains_from_halves_t16_kernel<<<grid_for(n_dom, 256, ctx->num_sms, 8), 256, 0, st>>>(
+                d_half, n_dom, ds, stride, d_domains);
+        else
+            domains_from_halves_kernel<<<grid_for(n_out, 256, ctx->num_sms, 8), 256, 0, st>>>(
+                d_half, n_out, N, ds, stride, d_domains);
         FWAV_LAUNCH_CHECK(ctx);
     } else {
         domains_generic_kernel<<<grid_for(n_out, 256, ctx->num_sms, 8), 256, 0, st>>>(

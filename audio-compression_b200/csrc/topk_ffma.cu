@@ -85,7 +85,8 @@ template <int ED, int TQ>
 __global__ void __launch_bounds__(kThreads, 1)
 topk_ffma_kernel(const float *__restrict__ Q, long long n_q, const float *__restrict__ E,
                  long long n_d, int top_k, int L, const uint8_t *__restrict__ active,
-                 int32_t *__restrict__ cand, float *__restrict__ scores) {
+                 int32_t *__restrict__ cand, float *__restrict__ scores,
+                 float *__restrict__ part_s, int32_t *__restrict__ part_i) {
     constexpr int C4 = ED / 4;                          // float4 columns per embedding row
     constexpr int PAD = C4 >= 8 ? 1 : 8 / C4;           // keeps the cp.async writes conflict-free
     constexpr int COLS = kStageRows + PAD;              // float4 per column per stage
@@ -106,6 +107,7 @@ topk_ffma_kernel(const float *__restrict__ Q, long long n_q, const float *__rest
             if (q < n_q && (!active || active[q])) any = 1;
         }
         if (!__syncthreads_or(any)) {
+            if (gridDim.y > 1) return;          // split launch: merge_split_kernel writes the -1 rows
             for (int i = threadIdx.x; i < QPB * top_k; i += kThreads) {
                 const long long q = (long long)blockIdx.x * QPB + i / top_k;
                 if (q < n_q) {
@@ -137,10 +139,13 @@ topk_ffma_kernel(const float *__restrict__ Q, long long n_q, const float *__rest
     for (int p = lane; p < TQ * L; p += 32) { my_s[p] = -INFINITY; my_i[p] = -1; }
     __syncwarp();
 
-    const long long n_tiles = (n_d + kStageRows - 1) / kStageRows;
+    // gridDim.y > 1: the table is split between several CTAs per query block (few queries, e.g. the fallback of
+    // the tensor-core search); each writes its partial top_k and merge_split_kernel merges them
+    const long long n_tiles_all = (n_d + kStageRows - 1) / kStageRows;
+    const long long t_lo = n_tiles_all * blockIdx.y / gridDim.y, n_tiles = n_tiles_all * (blockIdx.y + 1) / gridDim.y;
     auto issue = [&](long long tile) {
         if (tile < n_tiles) {
-            float4 *dst = stage + (tile % kStages) * (C4 * COLS);
+            float4 *dst = stage + ((tile - t_lo) % kStages) * (C4 * COLS);
             const long long row0 = tile * kStageRows;
 #pragma unroll
             for (int g = threadIdx.x; g < kStageRows * C4; g += kThreads) {
@@ -153,13 +158,13 @@ topk_ffma_kernel(const float *__restrict__ Q, long long n_q, const float *__rest
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) issue(s);
+    for (int s = 0; s < kStages - 1; ++s) issue(t_lo + s);
 
-    for (long long tile = 0; tile < n_tiles; ++tile) {
+    for (long long tile = t_lo; tile < n_tiles; ++tile) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
         issue(tile + kStages - 1);
-        const float4 *src = stage + (tile % kStages) * (C4 * COLS);
+        const float4 *src = stage + ((tile - t_lo) % kStages) * (C4 * COLS);
 #pragma unroll 1
         for (int j = 0; j < kStageRows / 32; ++j) {
             float e[ED];
@@ -206,10 +211,55 @@ topk_ffma_kernel(const float *__restrict__ Q, long long n_q, const float *__rest
                 rank += (ranks_before(so, io, s, i) || (so == s && io == i && o < p)) ? 1 : 0;
             }
             if (rank < top_k) {
-                cand[q * top_k + rank] = i;
-                if (scores) scores[q * top_k + rank] = s;
+                if (gridDim.y > 1) {
+                    const long long o = (q * gridDim.y + blockIdx.y) * top_k + rank;
+                    part_s[o] = s;
+                    part_i[o] = i;
+                } else {
+                    cand[q * top_k + rank] = i;
+                    if (scores) scores[q * top_k + rank] = s;
+                }
             }
         }
+    }
+}
+
+// merges the partial results of a split launch: one warp per query, top_k rounds of "best entry ranked after the
+// previous one" over n_split * top_k (score, index) entries; same total order as the kernel itself
+__global__ void __launch_bounds__(128)
+merge_split_kernel(const float *__restrict__ part_s, const int32_t *__restrict__ part_i, long long n_q, int n_split,
+                   int top_k, const uint8_t *__restrict__ active, int32_t *__restrict__ cand, float *__restrict__ scores) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 4 + warp;
+    if (q >= n_q) return;
+    const int n = n_split * top_k;
+    const float *ps = part_s + q * n;
+    const int32_t *pi = part_i + q * n;
+    const bool live = !active || active[q];
+    float prev_s = INFINITY;
+    int prev_i = -1;
+    for (int r = 0; r < top_k; ++r) {
+        float bs = -INFINITY;
+        int bi = -1;
+        if (live) {
+            for (int e = lane; e < n; e += 32) {
+                const float s = ps[e];
+                const int i = pi[e];
+                if (i < 0) continue;
+                if (ranks_before(prev_s, prev_i, s, i) && (bi < 0 || ranks_before(s, i, bs, bi))) { bs = s; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float os = __shfl_xor_sync(kFull, bs, o);
+                const int oi = __shfl_xor_sync(kFull, bi, o);
+                if (oi >= 0 && (bi < 0 || ranks_before(os, oi, bs, bi))) { bs = os; bi = oi; }
+            }
+        }
+        if (lane == 0) {
+            cand[q * top_k + r] = bi;
+            if (scores) scores[q * top_k + r] = bi >= 0 ? bs : -INFINITY;
+        }
+        if (bi >= 0) { prev_s = bs; prev_i = bi; }
     }
 }
 
@@ -224,9 +274,33 @@ int launch(fwav_ctx *ctx, const float *d_q, int64_t n_q, const float *d_emb, int
     FWAV_CUDA(ctx, cudaFuncSetAttribute(topk_ffma_kernel<ED, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     const long long grid = (n_q + QPB - 1) / QPB;
-    topk_ffma_kernel<ED, TQ><<<(unsigned)grid, kThreads, smem, st>>>(d_q, n_q, d_emb, n_d, top_k, L, d_active,
-                                                                    d_cand, d_scores);
+    // few queries: split the table over several CTAs per query block so that the machine is full
+    const long long n_tiles = (n_d + kStageRows - 1) / kStageRows;
+    long long split = 1;
+    if (grid < ctx->num_sms) {
+        split = ctx->num_sms / grid;
+        if (split > 64) split = 64;
+        if (split > n_tiles / 8) split = n_tiles / 8;
+        if (split < 1) split = 1;
+    }
+    float *d_ps = nullptr;
+    int32_t *d_pi = nullptr;
+    if (split > 1) {
+        unsigned char *blk = nullptr;
+        const size_t half = (size_t)n_q * split * top_k * 4;
+        int rc = fwav_ws_reserve(ctx, WS_FFMA_PARTS, 2 * half, (void **)&blk);
+        if (rc) return rc;
+        d_ps = reinterpret_cast<float *>(blk);
+        d_pi = reinterpret_cast<int32_t *>(blk + half);
+    }
+    topk_ffma_kernel<ED, TQ><<<dim3((unsigned)grid, (unsigned)split), kThreads, smem, st>>>(
+        d_q, n_q, d_emb, n_d, top_k, L, d_active, d_cand, d_scores, d_ps, d_pi);
     FWAV_LAUNCH_CHECK(ctx);
+    if (split > 1) {
+        merge_split_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_ps, d_pi, n_q, (int)split, top_k, d_active, d_cand,
+                                                                    d_scores);
+        FWAV_LAUNCH_CHECK(ctx);
+    }
     return FWAV_OK;
 }
 

@@ -956,8 +956,11 @@ merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, lon
 
 }  // namespace
 
+// The list kernel keeps 48 candidates per row (top_k <= 32); the fast path collects ~256 per query and selects any
+// top_k up to 64 from them (BASELINE.json config 4), handing its rare failures to the FFMA kernel when top_k > 32.
 bool fwav_topk_umma_supported(int emb_dim, int top_k, int64_t n_q, int64_t n_d) {
-    return emb_dim == ED && top_k >= 1 && top_k <= 32 && n_q > 0 && n_d > 0;
+    if (emb_dim != ED || top_k < 1 || n_q <= 0 || n_d <= 0) return false;
+    return top_k <= 32 || (top_k <= 64 && n_d >= (1 << 16));
 }
 
 namespace {
@@ -1026,7 +1029,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                           int emb_dim, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores,
                           cudaStream_t st) {
     FWAV_REQUIRE(ctx, fwav_topk_umma_supported(emb_dim, top_k, n_q, n_d),
-                 "tensor-core search is built for emb_dim=16 and top_k<=32 (got %d, %d)", emb_dim, top_k);
+                 "tensor-core search is built for emb_dim=16 and top_k<=32 (<=64 from 65536 domains up) (got %d, %d)",
+                 emb_dim, top_k);
     FWAV_REQUIRE(ctx, n_d < (1ll << 31) - kDStage, "n_domains %lld does not fit the int32 match index", (long long)n_d);
     FWAV_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_emb)) & 15) == 0,
                  "embedding tables must be 16-byte aligned");
@@ -1049,7 +1053,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
-    const bool fast = n_d >= kFastMinDomains && !(mode_env && !strcmp(mode_env, "lists"));
+    const bool fast = n_d >= kFastMinDomains && (top_k > 32 || !(mode_env && !strcmp(mode_env, "lists")));
     ctx->search_fast_path = fast;
     if (!fast) {
         for (int k = 1; k <= 4; ++k)
@@ -1153,8 +1157,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             FWAV_LAUNCH_CHECK(ctx);
             pack_f16_tiles_kernel<<<grid_for(ctx, fp * 2 * kDTile * 2), 256, 0, st>>>(d_fq, n_fail, fp * 2, d_fqt, 1);
             FWAV_LAUNCH_CHECK(ctx);
-            if ((rc = launch_lists(ctx, d_fqt, d_et, d_fq, d_emb, n_fail, n_d, (int)n_stages, top_k, nullptr, d_fc, d_fs, dbg, st)))
-                return rc;
+            if (top_k <= 32)
+                rc = launch_lists(ctx, d_fqt, d_et, d_fq, d_emb, n_fail, n_d, (int)n_stages, top_k, nullptr, d_fc, d_fs, dbg, st);
+            else
+                rc = fwav_launch_topk_ffma(ctx, d_fq, n_fail, d_emb, n_d, ED, top_k, nullptr, d_fc, d_fs, st);
+            if (rc) return rc;
             scatter_cand_kernel<<<(n_fail * top_k + 255) / 256, 256, 0, st>>>(d_fc, d_fs, d_fail, n_fail, top_k,
                                                                                d_cand + q0 * top_k,
                                                                                d_scores ? d_scores + q0 * top_k : nullptr);

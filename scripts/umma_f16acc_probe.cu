@@ -1,0 +1,164 @@
+// umma_f16acc_probe.cu — exploratory: tcgen05.mma kind::f16 with HALF-PRECISION accumulators.
+// Questions (B200, sm_100a): does D=F16 run at N=256, how do the 256 results of a row sit in TMEM (one per
+// 32-bit column, or two packed), what does tcgen05.ld ...pack::16b return, how accurate is the result, and
+// how fast is the instruction.  One CTA, one MMA on recognisable data, TMEM dumped raw to the host.
+//
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o umma_f16acc_probe umma_f16acc_probe.cu
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 22)) __trap();
+    }
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes contiguous; LBO between the two K chunks, SBO between 8-row groups
+__device__ __forceinline__ uint64_t desc_none(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+#define R32(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+               "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
+               "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
+               "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+
+// mode bit 0: D format (0 = f16 accumulators, 1 = f32); bit 1: use tcgen05.ld ... pack::16b for the dump
+__global__ void __launch_bounds__(160) probe_kernel(const __half *A, const __half *B, uint32_t *dump, long long *cycles,
+                                                    int mode, int n_rep) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __half *sa = reinterpret_cast<__half *>(smem);             // 128 x 16
+    __half *sb = reinterpret_cast<__half *>(smem + 4096);      // 256 x 16
+    const uint32_t bar = smem_u32(smem + 4096 + 8192);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 4096 + 8192 + 16);
+    // stage operands in the canonical no-swizzle K-major layout
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+        const int r = i / 16, k = i % 16;
+        sa[(k / 8) * (128 * 8) + (r / 8) * 64 + (r % 8) * 8 + (k % 8)] = A[i];
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const int r = i / 16, k = i % 16;
+        sb[(k / 8) * (256 * 8) + (r / 8) * 64 + (r % 8) * 8 + (k % 8)] = B[i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (warp == 4 && lane == 0) {
+        const uint32_t c_fmt = (mode & 1) ? 1u : 0u;
+        const uint32_t idesc = (c_fmt << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t da = desc_none(smem_u32(sa), 128 * 16, 128), db = desc_none(smem_u32(sb), 256 * 16, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < n_rep; ++i)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(0)
+                         : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        mbar_wait(bar, 0);
+        cycles[0] = clock64() - t0;
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        // dump the first 256 columns of this warp's 32 lanes: dump[row][col]
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            if (mode & 2)
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : R32(v) : "r"(ta) : "memory");
+            else
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : R32(v) : "r"(ta) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dump[(warp * 32 + lane) * 256 + c0 + j] = v[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+__global__ void max3_h2_probe(const uint32_t *in, uint32_t *out) {
+    // does a 3-input packed-half max exist?
+    uint32_t a = in[0], b = in[1], c = in[2], d;
+    asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(d), "r"(c));
+    out[0] = d;
+}
+
+int main(int argc, char **argv) {
+    const int mode = argc > 1 ? atoi(argv[1]) : 0;
+    const int n_rep = argc > 2 ? atoi(argv[2]) : 1;
+    __half hA[128 * 16], hB[256 * 16];
+    // A[r][0] = 1, A[r][1] = r/128 : D[r][n] = B[n][0] + (r/128) * B[n][1]
+    for (int r = 0; r < 128; ++r)
+        for (int k = 0; k < 16; ++k) hA[r * 16 + k] = __float2half(k == 0 ? 1.0f : k == 1 ? r / 128.0f : 0.0f);
+    // B[n][0] = n (exact in fp16 up to 2048), B[n][1] = 1/64
+    for (int n = 0; n < 256; ++n)
+        for (int k = 0; k < 16; ++k) hB[n * 16 + k] = __float2half(k == 0 ? (float)n : k == 1 ? 1.0f / 64 : 0.0f);
+    __half *dA, *dB;
+    uint32_t *dD;
+    long long *dC;
+    cudaMalloc(&dA, sizeof hA); cudaMalloc(&dB, sizeof hB); cudaMalloc(&dD, 128 * 256 * 4); cudaMalloc(&dC, 8);
+    cudaMemcpy(dA, hA, sizeof hA, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB, sizeof hB, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xEE, 128 * 256 * 4);
+    probe_kernel<<<1, 160, 4096 + 8192 + 64>>>(dA, dB, dD, dC, mode, n_rep);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+    static uint32_t hD[128 * 256];
+    long long cyc;
+    cudaMemcpy(hD, dD, sizeof hD, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
+    printf("mode %d (D=%s, ld %s), %d MMA: %lld cycles\n", mode, (mode & 1) ? "f32" : "f16", (mode & 2) ? "pack::16b" : "plain", n_rep, cyc);
+    for (int r : {0, 1, 64, 127}) {
+        printf("row %3d raw cols 0..7:", r);
+        for (int c = 0; c < 8; ++c) printf(" %08x", hD[r * 256 + c]);
+        printf("  | cols 126..131:");
+        for (int c = 126; c < 132; ++c) printf(" %08x", hD[r * 256 + c]);
+        printf("\n");
+        printf("        as halves (lo,hi) cols 0..5:");
+        for (int c = 0; c < 6; ++c) {
+            __half_raw lo, hi; lo.x = hD[r * 256 + c] & 0xffff; hi.x = hD[r * 256 + c] >> 16;
+            printf(" (%g,%g)", __half2float(__half(lo)), __half2float(__half(hi)));
+        }
+        printf("   as f32 cols 0..3:");
+        for (int c = 0; c < 4; ++c) { float f; memcpy(&f, &hD[r * 256 + c], 4); printf(" %g", f); }
+        printf("\n");
+    }
+    return 0;
+}

@@ -405,6 +405,25 @@ def test_search_paths_agree(ctx, monkeypatch):
             set_impl(ctx, "auto")
         return d_cand.to_host((n_q, K), np.int32), d_sc.to_host((n_q, K), np.float32)
 
+    # top_k = 64 (BASELINE.json config 4): only the fast path of the tensor-core search takes it
+    K64 = 64
+
+    def run64(impl, n_q):
+        monkeypatch.delenv("FWAV_UMMA_MODE", raising=False)
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * K64 * 4), ctx.alloc(n_q * K64 * 4)
+        try:
+            ctx.topk(d_emb.ptr, n_q, d_emb.ptr, n_d, ED, K64, None, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        return d_cand.to_host((n_q, K64), np.int32), d_sc.to_host((n_q, K64), np.float32)
+
+    w64, ws64 = run64("ffma", 2000)
+    before = ctx.search_fallbacks()
+    g64, gs64 = run64("umma", 2000)
+    assert np.array_equal(g64, w64) and np.array_equal(bits(gs64), bits(ws64))
+    print(f"top_k=64, n_q=2000: equal to FFMA; {ctx.search_fallbacks() - before} queries went to the fallback")
+
     for n_q in (5000, 300):          # 300 queries: two CTA pairs, so the list kernel splits the table
         mask = rng.random(n_q) > 0.2
         mask[256:512] = False        # a whole CTA pair pruned
