@@ -1,17 +1,16 @@
 // topk_umma.cu — A4 on the 5th-generation tensor cores: exact cosine-similarity
-// candidate search as a fused split-fp16 tcgen05 contraction with an in-kernel
-// threshold top-K (replaces range_candidates_from_embedding_emb,
-// /root/reference/fractal.py:535-552, for all ranges at once).
+// candidate search as a fused split-fp16 tcgen05 contraction (replaces
+// range_candidates_from_embedding_emb, /root/reference/fractal.py:535-552, for all
+// ranges at once).
 //
-// Shape of the work: scores = Q (n_q x 16) . E^T (16 x n_d), n_d ~ 2e6..4e7, top
-// 32 per row.  K = 16 is tiny, so the contraction is "all epilogue": every score
-// has to be looked at once, and a tcgen05.mma with so little K is bound by its
-// per-instruction cost, not by the tensor array (scripts/umma_microbench.cu on B200:
-// 118 cycles for M=128 N=128 K=16 whatever the operand layout, 173 for the CTA-pair
-// M=256 N=256 one that does four times the work).  The design therefore uses the
-// largest instruction there is and keeps the tensor pipe and the epilogue warps
-// both busy without ever writing a score to memory:
+// Shape of the work: scores = Q (n_q x 16) . E^T (16 x n_d), n_d ~ 2e6..9e7, top
+// 32 (or 64) per row.  K = 16 is tiny, so the contraction is "all epilogue": every
+// score has to leave TMEM and be looked at once, and a tcgen05.mma with so little K
+// is bound by its per-instruction cost, not by the tensor array
+// (scripts/umma_microbench.cu on B200: 118 cycles for M=128 N=128 K=16 whatever the
+// operand layout, 173 for the CTA-pair M=256 N=256 one that does four times the work).
 //
+// One kernel skeleton (scan_kernel<MODE>), shared by three epilogues:
 //   * a CLUSTER OF TWO CTAs (one TPC) owns 256 queries, 128 per CTA, and issues
 //     tcgen05.mma.cta_group::2 with M=256, N=256: each CTA keeps its own 128 query
 //     rows (A) and HALF of every 256-domain stage (B) in shared memory, so every
@@ -20,26 +19,25 @@
 //     bits) and pre-tiled by a pack kernel into the K-major SWIZZLE_32B UMMA layout,
 //     so one plain bulk copy (cp.async.bulk, the TMA engine, no tensor map) lands a
 //     128-domain tile in shared memory ready for the tensor core;
-//   * per stage the leader CTA's elected thread issues three K=16 instructions
-//     (hi*lo, lo*hi, hi*hi) into one of two 256-column TMEM accumulator buffers and
-//     commits to mbarriers in BOTH CTAs (multicast); the peer CTA relays "my half
-//     of the stage has landed" to the leader with a remote mbarrier arrive;
-//   * 8 epilogue warps per CTA (two per TMEM lane quadrant, 128 columns each) read
-//     the accumulators with tcgen05.ld 32x32b.x32 — one query row per thread — in two
-//     halves so that the second half's loads overlap the first half's reduction,
-//     hand the buffer back to the MMA thread as soon as it is in registers, reduce
-//     each 32-column chunk to its maximum with 3-input max instructions and compare
-//     it with the row's running threshold; only chunks that beat it take the
-//     warp-cooperative insertion path into the row's candidate list in shared memory
-//     (two warps share a row's list, under a per-quadrant lock);
-//   * a row keeps its 48 best candidates (top_k <= 32 plus a 16-entry margin) as
-//     sorted 64-bit keys; at the end every kept candidate is re-scored with the
-//     canonical float32 FMA chain and the best top_k are written best-first, so the
-//     result equals the FFMA kernel's unless more than 16 domains tie with the K-th
-//     score at the split-fp16 rounding level (~1e-6).
+//   * per stage three K=16 instructions (hi*lo, lo*hi, hi*hi) go into one of two
+//     256-column TMEM accumulator buffers; two issuing threads in the leader CTA,
+//     one per buffer; commits are multicast to the mbarriers of BOTH CTAs; the peer
+//     CTA relays "my half of the stage has landed" with a remote mbarrier arrive;
+//   * epilogue warps read the accumulators with tcgen05.ld 32x32b.x32 — one query
+//     row per thread — hand the buffer back as soon as their share is in registers,
+//     reduce each 32-column chunk to its maximum with 3-input max instructions and
+//     compare it with the row's threshold; only chunks that reach it do more.
+//
+// MODE_LISTS keeps an exact running top-K in shared memory (small tables, fallback);
+// MODE_THETA + MODE_COLLECT + finalize_kernel are the fast path: a per-query
+// threshold from a strided sample of the table, one scan that only appends the
+// indices of the domains that reach it, then an exact re-score with a proof that
+// nothing was missed.  Either way every returned candidate carries the canonical
+// float32 score (ascending-k FMA chain) and the rows are ordered by it, ties by
+// index: the result equals the FFMA kernel's bit for bit.
 //
 // Bound: tensor pipe, 2*16 algorithmic flop per pair (the split issues 3x that);
-// see DESIGN.md for the epilogue budget.
+// what actually limits it today is in DESIGN.md 4.3.
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
