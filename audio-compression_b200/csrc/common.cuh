@@ -25,6 +25,7 @@ struct fwav_ctx {
     cudaEvent_t search_ev[kSearchSlots][kSearchPhases + 1] = {};
     int search_slots_used = 0;
     bool search_fast_path = false;
+    bool search_hi_only = false;          // last collect pass filtered with the hi*hi term alone
 
     // embedding matrices cached per (N, half)
     int emb_N = 0, emb_half = 0;

@@ -104,6 +104,7 @@ struct ScanArgs {
     int32_t *cand;             // MODE_LISTS out
     float *scores;             // MODE_LISTS out (optional)
     float *theta;              // MODE_THETA out, MODE_COLLECT in
+    float *theta_hi;           // MODE_THETA out: the (top_k / 16)-th best sampled score (about the top_k-th of the table)
     int32_t *cbuf;             // MODE_COLLECT out: [query][column group][cap] domain indices
     int *ccount;               // MODE_COLLECT out: [query][column group] how many passed (may exceed cap)
     int cap;
@@ -444,8 +445,13 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
             a.trace[((t) - kTraceFrom) * 8 + (slot)] = clock64();                                     \
     } while (0)
 
-template <int MODE>
+// HI: only the hi*hi term (one MMA per stage, half the operand bytes).  Its scores are off by up to
+// kHiOnlySlack, which a FILTER can afford when the data leave that much room between the top_k-th score and the
+// threshold (decided per launch from pass 1, verified per query by finalize_kernel); MODE_LISTS never uses it.
+template <int MODE, bool HI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+    static_assert(!(HI && MODE == MODE_LISTS), "the exact list kernel needs the full split");
+    constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;      // bytes of a tile this launch reads
     constexpr int kEpi = epi_warps(MODE), kThreads = n_threads(MODE);
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -487,7 +493,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 for (int i = threadIdx.x; i < kQTile; i += kThreads) {
                     const long long q = q_base + i;
                     if (q >= n_q) continue;
-                    if (MODE == MODE_THETA) a.theta[q] = INFINITY;
+                    if (MODE == MODE_THETA) { a.theta[q] = INFINITY; a.theta_hi[q] = INFINITY; }
                     if (MODE == MODE_COLLECT) { for (int g = 0; g < 4; ++g) a.ccount[4 * q + g] = 0; }
                 }
             }
@@ -530,16 +536,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
     if (warp == kEpi) {
         // ===== producer: bulk copies (TMA engine) of this CTA's query tile and its half of every stage =====
         if (lane == 0) {
-            mbar_expect_tx(bar_a, kTileBytes);
-            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (2ll * pair_id + cta_rank) * (kTileBytes / 16), kTileBytes, bar_a);
+            mbar_expect_tx(bar_a, kOpBytes);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (2ll * pair_id + cta_rank) * (kTileBytes / 16), kOpBytes, bar_a);
             int tt = t_first;
             for (int t = 0; t < n_visit; ++t) {
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * s, kTileBytes);
+                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
                 bulk_g2s(smem_u32(smem + kOffB + s * kTileBytes),
-                         a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kTileBytes, bar_full + 8 * s);
+                         a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kOpBytes, bar_full + 8 * s);
                 if (++tt == s_hi) tt = s_lo;
             }
         }
@@ -579,9 +585,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 FWAV_TRACE(1, t);
                 tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
-                umma_f16_pair(d, da_hi, db_lo, 0);
-                umma_f16_pair(d, da_lo, db_hi, 1);
-                umma_f16_pair(d, da_hi, db_hi, 1);
+                if (HI) {
+                    umma_f16_pair(d, da_hi, db_hi, 0);
+                } else {
+                    umma_f16_pair(d, da_hi, db_lo, 0);
+                    umma_f16_pair(d, da_lo, db_hi, 1);
+                    umma_f16_pair(d, da_hi, db_hi, 1);
+                }
                 umma_commit_pair(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
                 umma_commit_pair(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
                 FWAV_TRACE(2, t);
@@ -710,6 +720,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                     if (x > tm[kTheta - 1]) insert_desc(tm, x);
                 }
                 a.theta[q] = tm[kTheta - 1];      // +inf for pruned rows, -inf if the sample was too small
+                int hi_rank = top_k / 16 - 1;
+                hi_rank = hi_rank < 0 ? 0 : hi_rank > kTheta - 1 ? kTheta - 1 : hi_rank;
+                float th = tm[0];
+#pragma unroll
+                for (int i = 1; i < kTheta; ++i) th = i == hi_rank ? tm[i] : th;
+                a.theta_hi[q] = hi_rank == 0 ? tm[0] : th;
             }
         } else {
             // both warps of a quadrant are done with their lists before the rows are finalised
@@ -788,7 +804,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
 // that fail (too few candidates, buffer overflow, boundary within the slack) go
 // on the list for the exact MODE_LISTS kernel.
 // ---------------------------------------------------------------------------
-constexpr float kScoreSlack = 4e-6f;   // bound on |tensor-core score - canonical float32 score| (measured max 3.9e-7)
+constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core score - canonical float32 score| (measured max 3.9e-7)
+// hi*hi term alone: inputs rounded to fp16 (relative 2^-11 each), sum |q_k e_k| <= |q||e| <= 2 (two unit heads):
+// 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
+constexpr float kHiOnlySlack = 2e-3f;
 constexpr int kFinWarps = 4;
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
@@ -803,7 +822,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x)
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
                 const uint8_t *__restrict__ active, const float *__restrict__ theta, const int32_t *__restrict__ cbuf,
-                const int *__restrict__ ccount, int cap, int32_t *__restrict__ cand, float *__restrict__ scores,
+                const int *__restrict__ ccount, int cap, float slack, int32_t *__restrict__ cand, float *__restrict__ scores,
                 int *__restrict__ fail_list, int *__restrict__ fail_count) {
     extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][4 * cap]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -871,7 +890,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
             last = unorder_bits((uint32_t)(best >> 32));
             ++n_sel;
         }
-        ok = n_sel == want && last >= theta[q] + kScoreSlack;
+        ok = n_sel == want && last >= theta[q] + slack;
         for (int i = want + lane; i < top_k; i += 32) {      // table smaller than top_k: pad like the reference
             cand[q * top_k + i] = -1;
             if (scores) scores[q * top_k + i] = -INFINITY;
@@ -881,6 +900,22 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         fail_list[atomicAdd(fail_count, 1)] = (int)q;
         atomicAdd(fail_count + (overflow ? 1 : n_sel < top_k ? 2 : 3), 1);      // diagnostics: why
     }
+}
+
+// After pass 1: how many live queries leave less than `room` between their estimated top_k-th score and theta?
+// Few: the collect pass may filter with the hi*hi term alone.  (A wrong guess costs fallbacks, never correctness.)
+__global__ void count_flat_kernel(const float *__restrict__ theta, const float *__restrict__ theta_hi, long long n_q,
+                                  float room, int *__restrict__ counts) {
+    int flat = 0, live = 0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n_q; q += (long long)gridDim.x * blockDim.x) {
+        const float t = theta[q];
+        if (t == INFINITY) continue;            // pruned
+        ++live;
+        flat += (theta_hi[q] - t < room) ? 1 : 0;
+    }
+    flat = __reduce_add_sync(0xffffffffu, flat);
+    live = __reduce_add_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(counts, flat); atomicAdd(counts + 1, live); }
 }
 
 // fallback plumbing: the failed queries as a dense table, and their results back in place
@@ -974,9 +1009,10 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
 }
 
 int set_smem_attrs(fwav_ctx *ctx) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_LISTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLists));
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_THETA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTheta));
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_LISTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLists));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_THETA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTheta));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
     return FWAV_OK;
 }
 
@@ -1011,7 +1047,7 @@ int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const floa
         int rc;
         if ((rc = fwav_ws_reserve(ctx, WS_UMMA_PARTS, (size_t)n_q * split * 2 * kCap * 8, (void **)&a.parts))) return rc;
     }
-    scan_kernel<MODE_LISTS><<<(unsigned)(2 * q_pairs * split), n_threads(MODE_LISTS), kSmemLists, st>>>(a);
+    scan_kernel<MODE_LISTS, false><<<(unsigned)(2 * q_pairs * split), n_threads(MODE_LISTS), kSmemLists, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     if (split > 1) {
         merge_parts_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_q, d_emb, n_q, (int)split, top_k, d_active, a.parts,
@@ -1076,7 +1112,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
     int *d_cnt = nullptr, *d_fail = nullptr;
-    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)n_q * sizeof(float), (void **)&d_theta))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 4) * sizeof(float), (void **)&d_theta))) return rc;
+    float *d_theta_hi = d_theta + n_q;
+    int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * kCollectCap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
@@ -1092,18 +1130,39 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.q_tiles = d_qt + (q0 / kQTile) * (kTileBytes / 16);
         a.e_tiles = d_et; a.Q = d_q + q0 * ED; a.E = d_emb; a.n_q = nq; a.n_d = n_d;
         a.n_stages = (int)n_stages; a.top_k = top_k; a.active = d_active ? d_active + q0 : nullptr;
-        a.theta = d_theta + q0; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = kCollectCap; a.dbg = dbg;
+        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = kCollectCap; a.dbg = dbg;
         a.n_split = 1;
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
-        scan_kernel<MODE_THETA><<<(unsigned)(2 * pairs), n_threads(MODE_THETA), kSmemTheta, st>>>(a);
+        // pass 1 keeps the full split: on data whose scores crowd together a threshold that is off by the hi*hi
+        // error (1e-3) lands hundreds of ranks away from where it should
+        scan_kernel<MODE_THETA, false><<<(unsigned)(2 * pairs), n_threads(MODE_THETA), kSmemTheta, st>>>(a);
         FWAV_LAUNCH_CHECK(ctx);
+        // may pass 2 filter with the hi*hi term too?  Only if (nearly) every query has room for its error bound
+        bool hi_only = false;
+        if (!(mode_env && !strcmp(mode_env, "precise"))) {
+            FWAV_CUDA(ctx, cudaMemsetAsync(d_flat, 0, 2 * sizeof(int), st));
+            count_flat_kernel<<<grid_for(ctx, nq), 256, 0, st>>>(d_theta + q0, d_theta_hi + q0, nq, 2.0f * kHiOnlySlack, d_flat);
+            FWAV_LAUNCH_CHECK(ctx);
+            int h_flat[2] = {0, 0};
+            FWAV_CUDA(ctx, cudaMemcpyAsync(h_flat, d_flat, sizeof h_flat, cudaMemcpyDeviceToHost, st));
+            FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+            hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.005 * h_flat[1];
+            if (mode_env && !strcmp(mode_env, "hionly")) hi_only = true;
+            if (getenv("FWAV_UMMA_VERBOSE"))
+                fprintf(stderr, "[fwav] search batch at %lld: %d of %d live queries leave < %.1e between their top_k-th score and theta: %s collect pass\n",
+                        q0, h_flat[0], h_flat[1], 2.0 * kHiOnlySlack, hi_only ? "hi*hi-only" : "full-split");
+        }
+        ctx->search_hi_only = hi_only;
         if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {
             if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, kTraceStages * 8 * sizeof(long long), (void **)&a.trace))) return rc;
             FWAV_CUDA(ctx, cudaMemsetAsync(a.trace, 0, kTraceStages * 8 * sizeof(long long), st));
         }
-        scan_kernel<MODE_COLLECT><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
+        if (hi_only)
+            scan_kernel<MODE_COLLECT, true><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
+        else
+            scan_kernel<MODE_COLLECT, false><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
         FWAV_LAUNCH_CHECK(ctx);
         if ((rc = mark(ctx, slot, 3, st))) return rc;
         if (dbg & 64) {
@@ -1125,7 +1184,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         finalize_kernel<<<(unsigned)((nq + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
                           (size_t)kFinWarps * 4 * kCollectCap * sizeof(unsigned long long), st>>>(
             d_q + q0 * ED, d_emb, nq, n_d, top_k, d_active ? d_active + q0 : nullptr, d_theta + q0, d_cbuf, d_cnt,
-            kCollectCap, d_cand + q0 * top_k, d_scores ? d_scores + q0 * top_k : nullptr, d_fail, d_fail_count);
+            kCollectCap, hi_only ? kHiOnlySlack : kScoreSlack, d_cand + q0 * top_k, d_scores ? d_scores + q0 * top_k : nullptr, d_fail, d_fail_count);
         FWAV_LAUNCH_CHECK(ctx);
         if ((rc = mark(ctx, slot, 4, st))) return rc;
         // NOTE: fail_list holds batch-local indices; resolve this batch's failures before the next one
