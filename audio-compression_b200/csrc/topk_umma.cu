@@ -72,24 +72,28 @@ constexpr uint32_t kTileBytes = 2 * kPartBytes;        // 8 KB: hi | lo
 constexpr uint32_t kSBO = 256;                         // bytes between 8-row groups (8 rows x 32 B)
 constexpr unsigned kFull = 0xffffffffu;
 
-// shared memory map (dynamic, 1024-aligned), identical in both CTAs of a pair
+enum { MODE_LISTS = 0, MODE_THETA = 1, MODE_COLLECT = 2 };
+
+// shared memory map (dynamic, 1024-aligned; identical in both CTAs of a pair):
+//   query tile | barriers | mode-specific area | ring of domain stages
 constexpr uint32_t kOffA = 0;
-constexpr uint32_t kOffB = kOffA + kTileBytes;
-constexpr uint32_t kOffList = kOffB + kStages * kTileBytes;
-constexpr uint32_t kOffBars = kOffList;                 // barriers first, so that their place does not depend on the mode
+constexpr uint32_t kOffBars = kOffA + kTileBytes;
 constexpr uint32_t kBarBytes = 16 * kStages + 72;      // full[], empty[], tfull[2], tempty[2], a, done[2], tmem slot
-constexpr uint32_t kOffMode = kOffBars + 256;          // mode-specific area
-// MODE_LISTS: [row][column half][kCap] keys, then one owner's 128 scores per warp
-constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
-constexpr uint32_t kSmemLists = kOffScratch + 8 * 128 * 4;
-// MODE_THETA: [row][kTheta] scores of column half 1 for the final merge of the two halves
+constexpr uint32_t kOffMode = kOffBars + 256;
+static_assert(kBarBytes <= 256, "barrier block");
 constexpr int kTheta = 16;             // threshold = kTheta-th largest score against the sample table
 constexpr int kThetaPart = 6;          // kept per column group (four groups per row)
-constexpr uint32_t kSmemTheta = kOffMode + kQTile * 3 * kThetaPart * 4;
-constexpr uint32_t kSmemCollect = kOffMode;
-static_assert(kBarBytes <= 256, "barrier block");
+// MODE_LISTS: [row][column half][kCap] keys, then one owner's 128 scores per warp
+constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
+// MODE_THETA: [row][3][kThetaPart] scores of column groups 1..3 for the final merge
+__host__ __device__ constexpr uint32_t mode_bytes(int mode) {
+    return mode == MODE_LISTS ? (kOffScratch - kOffMode) + 8 * 128 * 4 : mode == MODE_THETA ? kQTile * 3 * kThetaPart * 4 : 0;
+}
+__host__ __device__ constexpr uint32_t off_ring(int mode) { return (kOffMode + mode_bytes(mode) + 1023u) & ~1023u; }
+// a stage is 256 domains: one 8 KB tile per CTA of a pair, or both tiles (16 KB) in a CTA on its own
+__host__ __device__ constexpr uint32_t stage_bytes(int cg) { return cg == 1 ? 2 * kTileBytes : kTileBytes; }
+__host__ __device__ constexpr uint32_t smem_bytes(int mode, int cg) { return off_ring(mode) + kStages * stage_bytes(cg); }
 
-enum { MODE_LISTS = 0, MODE_THETA = 1, MODE_COLLECT = 2 };
 
 struct ScanArgs {
     const uint4 *q_tiles;      // packed query tiles (one per CTA)
@@ -114,12 +118,15 @@ struct ScanArgs {
 
 
 // UMMA instruction descriptor: D=F32, A=B=F16, both K-major, N=256, M=256 (cta_group::2)
-constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)(kQPair >> 4) << 24);
+constexpr uint32_t idesc_for(int cg) { return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)((kQTile * cg) >> 4) << 24); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -180,11 +187,15 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// completion of every MMA issued so far -> the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3)
-                 : "memory");
+// completion of every MMA issued so far -> the barrier at this offset (CG == 2: in BOTH CTAs of the pair)
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if (CG == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3)
+                     : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // K-major SWIZZLE_32B matrix descriptor (cute::UMMA::SmemDescriptor, version 1): 8-row groups
 // kSBO bytes apart, the two 16-byte K chunks of a row adjacent (leading offset 1)
@@ -192,14 +203,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(kSBO >> 4) << 32) |
            (1ull << 46) | (6ull << 61);
 }
-// D[tmem] (+)= A[smem] . B[smem]^T over the CTA pair, fp16 operands, K = 16, f32 accumulate
-__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 operands, K = 16, f32 accumulate; CG == 2: M = 256 over the CTA pair
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    if (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc_for(2)), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc_for(1)), "r"(accumulate)
+            : "memory");
 }
 
 #define FWAV_R32(v) "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
@@ -448,8 +468,15 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
 // HI: only the hi*hi term (one MMA per stage, half the operand bytes).  Its scores are off by up to
 // kHiOnlySlack, which a FILTER can afford when the data leave that much room between the top_k-th score and the
 // threshold (decided per launch from pass 1, verified per query by finalize_kernel); MODE_LISTS never uses it.
-template <int MODE, bool HI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+// CG: CTAs per tensor-core group.  2 = the pair described above (a domain tile is read once per 256 queries).
+// 1 = every CTA on its own (M = 128, the whole 256-domain stage in its shared memory, all barriers local: no relay,
+// no remote arrive, no multicast commit in the accumulator hand-over chain that bounds the streaming modes).
+template <int MODE, bool HI, int CG>
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+    constexpr int kQGroup = kQTile * CG;                             // queries per tensor-core group
+    constexpr uint32_t kStageBytes = stage_bytes(CG);                // B bytes per stage in this CTA's shared memory
+    constexpr uint32_t kOffB = off_ring(MODE);
+    constexpr uint32_t kLoOff = kStageBytes / 2;                     // hi parts first, lo parts behind them
     static_assert(!(HI && MODE == MODE_LISTS), "the exact list kernel needs the full split");
     constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;      // bytes of a tile this launch reads
     constexpr int kEpi = epi_warps(MODE), kThreads = n_threads(MODE);
@@ -458,10 +485,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
     const long long n_q = a.n_q, n_d = a.n_d;
     const int top_k = a.top_k, dbg = a.dbg;
     const uint8_t *__restrict__ active = a.active;
-    uint32_t cta_rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-    const int pair_id = (int)(blockIdx.x >> 1) / a.n_split, split = (int)(blockIdx.x >> 1) % a.n_split;
-    const long long pair_base = (long long)pair_id * kQPair;               // first query of the pair
+    uint32_t cta_rank = 0;
+    if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int pair_id = (int)(blockIdx.x / CG) / a.n_split, split = (int)(blockIdx.x / CG) % a.n_split;
+    const long long pair_base = (long long)pair_id * kQGroup;              // first query of the group
     const long long q_base = pair_base + (long long)cta_rank * kQTile;    // first query of this CTA
     unsigned long long *rows = reinterpret_cast<unsigned long long *>(smem + kOffMode);
     const uint32_t bars = smem_u32(smem + kOffBars);
@@ -474,7 +501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
     // take the same decision.
     {
         int any = 0;
-        for (int i = threadIdx.x; i < kQPair; i += kThreads) {
+        for (int i = threadIdx.x; i < kQGroup; i += kThreads) {
             const long long q = pair_base + i;
             if (q < n_q && (!active || active[q])) any = 1;
         }
@@ -505,23 +532,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
         for (int i = threadIdx.x; i < kQTile * 2 * kCap; i += kThreads) rows[i] = empty_key(i % kCap);
     if (threadIdx.x == 0) {
         // the leader's "stage has landed" barriers collect its own copy and the peer's relay
-        const uint32_t n_land = cta_rank == 0 ? 2u : 1u;
+        const uint32_t n_land = (CG == 2 && cta_rank == 0) ? 2u : 1u;
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, n_land); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * kEpi); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, CG * kEpi); }
         mbar_init(bar_a, n_land);
         mbar_init(bar_a + 8, 1);
         mbar_init(bar_a + 16, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpi) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();           // barriers of both CTAs are initialised before anyone arrives on them
+    if (CG == 2) cluster_sync_all();           // barriers of both CTAs are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Full scans visit the stages starting at the pair's own rows and wrapping around: when the
@@ -532,24 +562,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
     const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
     const int n_visit = s_hi - s_lo;
     const int t_first = s_lo + (int)((pair_base / kDStage) % n_visit);
+    constexpr uint32_t kStageStride = kStageBytes;
 
     if (warp == kEpi) {
         // ===== producer: bulk copies (TMA engine) of this CTA's query tile and its half of every stage =====
         if (lane == 0) {
             mbar_expect_tx(bar_a, kOpBytes);
-            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (2ll * pair_id + cta_rank) * (kTileBytes / 16), kOpBytes, bar_a);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + ((long long)CG * pair_id + cta_rank) * (kTileBytes / 16), kOpBytes, bar_a);
             int tt = t_first;
             for (int t = 0; t < n_visit; ++t) {
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
-                bulk_g2s(smem_u32(smem + kOffB + s * kTileBytes),
-                         a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kOpBytes, bar_full + 8 * s);
+                const uint32_t dst = smem_u32(smem + kOffB + s * kStageStride);
+                if (CG == 2) {
+                    // this CTA's half of the stage: its hi part, and right behind it its lo part
+                    mbar_expect_tx(bar_full + 8 * s, kOpBytes);
+                    bulk_g2s(dst, a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kOpBytes, bar_full + 8 * s);
+                } else {
+                    // both tiles of the stage: [hi 0 | hi 1] and, for the full split, [lo 0 | lo 1] behind them
+                    const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
+                    mbar_expect_tx(bar_full + 8 * s, 2 * kOpBytes);
+                    bulk_g2s(dst, t0, kPartBytes, bar_full + 8 * s);
+                    bulk_g2s(dst + kPartBytes, t1, kPartBytes, bar_full + 8 * s);
+                    if (!HI) {
+                        bulk_g2s(dst + kLoOff, t0 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
+                        bulk_g2s(dst + kLoOff + kPartBytes, t1 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
+                    }
+                }
                 if (++tt == s_hi) tt = s_lo;
             }
         }
-    } else if (cta_rank != 0 && warp > kEpi) {
+    } else if (CG == 2 && cta_rank != 0 && warp > kEpi) {
         // ===== peer CTA: tell the leader when this CTA's operands have landed =====
         if (warp == kEpi + 1 && lane == 0) {
             mbar_wait(bar_a, 0);
@@ -577,7 +621,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 const uint32_t tph = (uint32_t)((t >> 1) & 1);
-                const uint32_t b_hi = smem_u32(smem + kOffB + s * kTileBytes), b_lo = b_hi + kPartBytes;
+                const uint32_t b_hi = smem_u32(smem + kOffB + s * kStageStride), b_lo = b_hi + kLoOff;
                 const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_lo);
                 mbar_wait(bar_full + 8 * s, ph);                               // landed long ago, as a rule
                 FWAV_TRACE(0, t);
@@ -586,18 +630,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
                 if (HI) {
-                    umma_f16_pair(d, da_hi, db_hi, 0);
+                    umma_f16<CG>(d, da_hi, db_hi, 0);
                 } else {
-                    umma_f16_pair(d, da_hi, db_lo, 0);
-                    umma_f16_pair(d, da_lo, db_hi, 1);
-                    umma_f16_pair(d, da_hi, db_hi, 1);
+                    umma_f16<CG>(d, da_hi, db_lo, 0);
+                    umma_f16<CG>(d, da_lo, db_hi, 1);
+                    umma_f16<CG>(d, da_hi, db_hi, 1);
                 }
-                umma_commit_pair(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
-                umma_commit_pair(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
+                umma_commit<CG>(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
+                umma_commit<CG>(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
                 FWAV_TRACE(2, t);
             }
             if (dbg & 8) {   // free-running profiling mode: drain the tensor pipe before leaving
-                umma_commit_pair(bar_a + 8 + 8 * buf);
+                umma_commit<CG>(bar_a + 8 + 8 * buf);
                 mbar_wait(bar_a + 8 + 8 * buf, 0);
             }
         }
@@ -645,7 +689,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 // the whole stage sits in registers: hand the TMEM buffer back before looking at the rest
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0 && !((dbg & 32) && cta_rank)) mbar_arrive_remote(bar_tempty + 8 * buf, 0);   // dbg 32: timing experiment
+                if (lane == 0) { if (CG == 2) mbar_arrive_remote(bar_tempty + 8 * buf, 0); else mbar_arrive_local(bar_tempty + 8 * buf); }
                 const long long base = (long long)tt * kDStage + half * 128;
                 if (++tt == s_hi) tt = s_lo;
                 if (dbg & 3) continue;
@@ -662,14 +706,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
                 const uint32_t ta = t_lane + (uint32_t)(buf * kDStage);
                 uint32_t x0[32], x1[32];
                 tmem_ld32(ta, x0);
-                tmem_wait_ld1(x0);
-                tmem_ld32(ta + 32, x1);          // in flight while the first chunk is reduced: the four warps of a
-                const float ma = chunk_max(x0);  // scheduler then interleave TMEM-port and ALU time instead of
-                tmem_wait_ld1(x1);               // all loading first and all reducing afterwards
-                // this warp's share of the buffer is in registers: hand it back before looking at the rest
+                tmem_ld32(ta + 32, x1);
+                tmem_wait_ld2(x0, x1);
+                // this warp's share of the buffer is in registers: hand it back before looking at it (the hand-over
+                // chain MMA -> commit -> load -> arrive -> MMA is what bounds the scan, so nothing else goes in it)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+                if (lane == 0) { if (CG == 2) mbar_arrive_remote(bar_tempty + 8 * buf, 0); else mbar_arrive_local(bar_tempty + 8 * buf); }
+                const float ma = chunk_max(x0);
                 const int col0 = tt * kDStage + half * kCols;
                 if (++tt == s_hi) tt = s_lo;
                 const float mb = chunk_max(x1);
@@ -787,10 +831,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads(MODE), 1) 
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the other may still signal it
+    if (CG == 2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the other may still signal it
     if (warp == kEpi) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1008,11 +1055,17 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
     return (int)(need < cap ? need : cap);
 }
 
-int set_smem_attrs(fwav_ctx *ctx) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_LISTS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLists));
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_THETA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTheta));
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCollect));
+// one launch of the scan skeleton: `groups` tensor-core groups of 128 * CG queries, each scanned by `split` of them
+template <int MODE, bool HI, int CG>
+int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    constexpr int smem = (int)smem_bytes(MODE, CG);
+    static bool attr_set = false;          // per process; the attribute is per function, not per context
+    if (!attr_set) {
+        FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    scan_kernel<MODE, HI, CG><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
 
@@ -1047,8 +1100,7 @@ int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const floa
         int rc;
         if ((rc = fwav_ws_reserve(ctx, WS_UMMA_PARTS, (size_t)n_q * split * 2 * kCap * 8, (void **)&a.parts))) return rc;
     }
-    scan_kernel<MODE_LISTS, false><<<(unsigned)(2 * q_pairs * split), n_threads(MODE_LISTS), kSmemLists, st>>>(a);
-    FWAV_LAUNCH_CHECK(ctx);
+    { int rc = launch_scan<MODE_LISTS, false, 2>(ctx, a, q_pairs, split, st); if (rc) return rc; }
     if (split > 1) {
         merge_parts_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_q, d_emb, n_q, (int)split, top_k, d_active, a.parts,
                                                                     d_cand, d_scores);
@@ -1083,7 +1135,6 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     FWAV_LAUNCH_CHECK(ctx);
     pack_f16_tiles_kernel<<<grid_for(ctx, q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt, 1);
     FWAV_LAUNCH_CHECK(ctx);
-    if ((rc = set_smem_attrs(ctx))) return rc;
     const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
@@ -1108,6 +1159,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_MISC, (size_t)s_stages * 2 * kTileBytes, (void **)&d_es))) return rc;
     pack_f16_tiles_kernel<<<grid_for(ctx, s_stages * 2 * kDTile * 2), 256, 0, st>>>(d_emb, n_d, s_stages * 2, d_es, kSampleStride);
     FWAV_LAUNCH_CHECK(ctx);
+    const char *cg_env = getenv("FWAV_UMMA_CG");
+    const bool single = !(cg_env && atoi(cg_env) == 2);
     const long long batch = n_q < kBatchQueries ? n_q : kBatchQueries;
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
@@ -1135,8 +1188,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
         // pass 1 keeps the full split: on data whose scores crowd together a threshold that is off by the hi*hi
         // error (1e-3) lands hundreds of ranks away from where it should
-        scan_kernel<MODE_THETA, false><<<(unsigned)(2 * pairs), n_threads(MODE_THETA), kSmemTheta, st>>>(a);
-        FWAV_LAUNCH_CHECK(ctx);
+        // streaming modes: CTAs on their own by default (FWAV_UMMA_CG=2: CTA pairs)
+        const long long groups = single ? (nq + kQTile - 1) / kQTile : pairs;
+        if ((rc = single ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
+            return rc;
         // may pass 2 filter with the hi*hi term too?  Only if (nearly) every query has room for its error bound
         bool hi_only = false;
         if (!(mode_env && !strcmp(mode_env, "precise"))) {
@@ -1160,10 +1215,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             FWAV_CUDA(ctx, cudaMemsetAsync(a.trace, 0, kTraceStages * 8 * sizeof(long long), st));
         }
         if (hi_only)
-            scan_kernel<MODE_COLLECT, true><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
+            rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, a, groups, 1, st);
         else
-            scan_kernel<MODE_COLLECT, false><<<(unsigned)(2 * pairs), n_threads(MODE_COLLECT), kSmemCollect, st>>>(a);
-        FWAV_LAUNCH_CHECK(ctx);
+            rc = single ? launch_scan<MODE_COLLECT, false, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_COLLECT, false, 2>(ctx, a, groups, 1, st);
+        if (rc) return rc;
         if ((rc = mark(ctx, slot, 3, st))) return rc;
         if (dbg & 64) {
             static long long h_trace[kTraceStages * 8];
