@@ -41,7 +41,7 @@ struct fwav_ctx {
 // scratch slots
 enum {
     WS_HALF = 0, WS_ACTIVE, WS_CAND, WS_QEMB, WS_DECODE_A, WS_DECODE_RED, WS_UMMA_E, WS_UMMA_Q, WS_UMMA_MISC,
-    WS_UMMA_THETA, WS_UMMA_CBUF, WS_UMMA_CNT, WS_UMMA_FAIL, WS_UMMA_FB, WS_UMMA_PARTS, WS_FFMA_PARTS,
+    WS_UMMA_THETA, WS_UMMA_CBUF, WS_UMMA_CNT, WS_UMMA_FAIL, WS_UMMA_FB, WS_UMMA_PARTS, WS_FFMA_PARTS, WS_UMMA_TAIL,
     // device mirrors of the host-buffer entry points
     WS_H_SIGNAL, WS_H_RANGES, WS_H_DOMAINS, WS_H_EMB, WS_H_MATCH, WS_H_OUT,
     WS_COUNT

@@ -109,8 +109,8 @@ struct ScanArgs {
     float *scores;             // MODE_LISTS out (optional)
     float *theta;              // MODE_THETA out, MODE_COLLECT in
     float *theta_hi;           // MODE_THETA out: the (top_k / 16)-th best sampled score (about the top_k-th of the table)
-    int32_t *cbuf;             // MODE_COLLECT out: [query][column group][cap] domain indices
-    int *ccount;               // MODE_COLLECT out: [query][column group] how many passed (may exceed cap)
+    int32_t *cbuf;             // MODE_COLLECT out: [query][split][column group][cap] domain indices
+    int *ccount;               // MODE_COLLECT out: [query][split][column group] how many passed (may exceed cap)
     int cap;
     int dbg;
     long long *trace;          // profiling: clock64 stamps of pair 0's leader CTA, [stage][8] (dbg bit 64)
@@ -521,7 +521,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                     const long long q = q_base + i;
                     if (q >= n_q) continue;
                     if (MODE == MODE_THETA) { a.theta[q] = INFINITY; a.theta_hi[q] = INFINITY; }
-                    if (MODE == MODE_COLLECT) { for (int g = 0; g < 4; ++g) a.ccount[4 * q + g] = 0; }
+                    if (MODE == MODE_COLLECT) { for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0; }
                 }
             }
             return;
@@ -664,7 +664,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         int32_t *cbuf = nullptr;
         if (MODE == MODE_COLLECT) {
             tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;  // +inf for pruned rows (written by pass 1)
-            cbuf = a.cbuf + ((q < n_q ? q : 0) * 4 + half) * (long long)a.cap;
+            cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + half) * (long long)a.cap;
         }
         int tt = t_first;
         if (MODE == MODE_LISTS) {
@@ -744,7 +744,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
             }
         }
         if (MODE == MODE_COLLECT) {
-            if (q < n_q) a.ccount[4 * q + half] = cnt;
+            if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
         } else if (MODE == MODE_THETA) {
             // theta of a row = kTheta-th largest sampled score over the four column groups.  A group keeps
             // its own kThetaPart best, so if more than that many of the row's best sit in one group the
@@ -869,9 +869,9 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x)
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
                 const uint8_t *__restrict__ active, const float *__restrict__ theta, const int32_t *__restrict__ cbuf,
-                const int *__restrict__ ccount, int cap, float slack, int32_t *__restrict__ cand, float *__restrict__ scores,
-                int *__restrict__ fail_list, int *__restrict__ fail_count) {
-    extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][4 * cap]
+                const int *__restrict__ ccount, int cap, int parts, int q_index0, float slack, int32_t *__restrict__ cand,
+                float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count) {
+    extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][parts * cap]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * kFinWarps + warp;
     if (q >= n_q) return;
@@ -882,40 +882,43 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         }
         return;
     }
-    unsigned long long *keys = fin_keys + (size_t)warp * 4 * cap;
-    int cn[4], c = 0;
+    unsigned long long *keys = fin_keys + (size_t)warp * parts * cap;
+    int c = 0;
     bool ok = true, overflow = false;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        cn[g] = ccount[4 * q + g];
-        ok = ok && cn[g] <= cap;
-        c += cn[g];
+    for (int p = 0; p < parts; ++p) {                  // parts = 4 column groups x table splits
+        const int cn = ccount[q * parts + p];
+        ok = ok && cn <= cap;
+        c += cn;
     }
     overflow = !ok;
     int n_sel = 0;
     float last = -INFINITY;
     if (ok) {
-        const int32_t *b0 = cbuf + (q * 4) * (long long)cap;
-        const int e1 = cn[0], e2 = e1 + cn[1], e3 = e2 + cn[2];
         float qv[ED];
 #pragma unroll
         for (int k = 0; k < ED; k += 4) {
             const float4 f = __ldg(reinterpret_cast<const float4 *>(Q + q * ED + k));
             qv[k] = f.x; qv[k + 1] = f.y; qv[k + 2] = f.z; qv[k + 3] = f.w;
         }
-        for (int i = lane; i < c; i += 32) {
-            const int id = i < e1 ? b0[i] : i < e2 ? b0[cap + i - e1] : i < e3 ? b0[2 * cap + i - e2] : b0[3 * cap + i - e3];
-            unsigned long long key = 0ull;                 // below every real key: padded columns
-            if (id < n_d) {
-                float ev[ED];
+        int off = 0;
+        for (int p = 0; p < parts; ++p) {
+            const int cn = ccount[q * parts + p];
+            const int32_t *b = cbuf + (q * parts + p) * (long long)cap;
+            for (int i = lane; i < cn; i += 32) {
+                const int id = b[i];
+                unsigned long long key = 0ull;                 // below every real key: padded columns
+                if (id < n_d) {
+                    float ev[ED];
 #pragma unroll
-                for (int k = 0; k < ED; k += 4) {
-                    const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
-                    ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
+                    for (int k = 0; k < ED; k += 4) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
+                        ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
+                    }
+                    key = make_key(fwm::score_chain(qv, ev, ED), id);
                 }
-                key = make_key(fwm::score_chain(qv, ev, ED), id);
+                keys[off + i] = key;
             }
-            keys[i] = key;
+            off += cn;
         }
         __syncwarp();
         // top_k rounds of "largest key below the previous one"
@@ -944,7 +947,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         }
     }
     if (!ok && lane == 0) {
-        fail_list[atomicAdd(fail_count, 1)] = (int)q;
+        fail_list[atomicAdd(fail_count, 1)] = (int)q + q_index0;
         atomicAdd(fail_count + (overflow ? 1 : n_sel < top_k ? 2 : 3), 1);      // diagnostics: why
     }
 }
@@ -1214,11 +1217,45 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, kTraceStages * 8 * sizeof(long long), (void **)&a.trace))) return rc;
             FWAV_CUDA(ctx, cudaMemsetAsync(a.trace, 0, kTraceStages * 8 * sizeof(long long), st));
         }
-        if (hi_only)
-            rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, a, groups, 1, st);
-        else
-            rc = single ? launch_scan<MODE_COLLECT, false, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_COLLECT, false, 2>(ctx, a, groups, 1, st);
-        if (rc) return rc;
+        // The last, partial wave of CTAs would take as long as a full one: split the table between several CTAs
+        // per 128 queries there (own candidate buffers, `parts` = 4 x splits), so that the tail takes 1/splits.
+        long long main_groups = groups, tail_groups = 0, tail_split = 1;
+        if (single && !dbg && groups > ctx->num_sms) {
+            const long long rem = groups % ctx->num_sms;
+            if (rem > 0 && rem <= ctx->num_sms / 2) {
+                tail_split = ctx->num_sms / rem;
+                if (tail_split > 8) tail_split = 8;
+                if (tail_split >= 2) { tail_groups = rem; main_groups = groups - rem; } else tail_split = 1;
+            }
+        }
+        const long long main_q = tail_groups ? main_groups * kQTile : nq;
+        const int tail_cap = kCollectCap / 2;      // a split sees 1/tail_split of the table: ~256 / (4 * tail_split) hits per part expected
+        ScanArgs at = a;
+        if (tail_groups) {
+            int32_t *d_tbuf = nullptr;
+            const long long tq = nq - main_q;
+            const size_t nb = (size_t)tq * tail_split * 4 * tail_cap * sizeof(int32_t), nc = (size_t)tq * tail_split * 4 * sizeof(int);
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_tbuf))) return rc;
+            a.n_q = main_q;
+            at.q_tiles = a.q_tiles + main_groups * (kTileBytes / 16);
+            at.Q = a.Q + main_q * ED;
+            at.active = a.active ? a.active + main_q : nullptr;
+            at.theta = a.theta + main_q;
+            at.n_q = tq;
+            at.n_split = (int)tail_split;
+            at.cbuf = d_tbuf;
+            at.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_tbuf) + nb);
+            at.cap = tail_cap;
+        }
+        for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
+            const ScanArgs &ax = part ? at : a;
+            const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
+            if (hi_only)
+                rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);
+            else
+                rc = single ? launch_scan<MODE_COLLECT, false, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, false, 2>(ctx, ax, g, sp, st);
+            if (rc) return rc;
+        }
         if ((rc = mark(ctx, slot, 3, st))) return rc;
         if (dbg & 64) {
             static long long h_trace[kTraceStages * 8];
@@ -1236,11 +1273,20 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 fclose(f);
             }
         }
-        finalize_kernel<<<(unsigned)((nq + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
-                          (size_t)kFinWarps * 4 * kCollectCap * sizeof(unsigned long long), st>>>(
-            d_q + q0 * ED, d_emb, nq, n_d, top_k, d_active ? d_active + q0 : nullptr, d_theta + q0, d_cbuf, d_cnt,
-            kCollectCap, hi_only ? kHiOnlySlack : kScoreSlack, d_cand + q0 * top_k, d_scores ? d_scores + q0 * top_k : nullptr, d_fail, d_fail_count);
-        FWAV_LAUNCH_CHECK(ctx);
+        for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
+            const ScanArgs &ax = part ? at : a;
+            const long long qoff = part ? main_q : 0;
+            const int parts = 4 * ax.n_split;
+            const size_t fin_smem = (size_t)kFinWarps * parts * ax.cap * sizeof(unsigned long long);
+            if (fin_smem > 48 * 1024)
+                FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+            finalize_kernel<<<(unsigned)((ax.n_q + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
+                              fin_smem, st>>>(
+                ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
+                hi_only ? kHiOnlySlack : kScoreSlack, d_cand + (q0 + qoff) * top_k,
+                d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count);
+            FWAV_LAUNCH_CHECK(ctx);
+        }
         if ((rc = mark(ctx, slot, 4, st))) return rc;
         // NOTE: fail_list holds batch-local indices; resolve this batch's failures before the next one
         int h_fail[4] = {0, 0, 0, 0};
