@@ -83,6 +83,7 @@ constexpr uint32_t kOffMode = kOffBars + 256;
 static_assert(kBarBytes <= 256, "barrier block");
 constexpr int kTheta = 16;             // threshold = kTheta-th largest score against the sample table
 constexpr int kThetaPart = 6;          // kept per column group (four groups per row)
+constexpr int kThetaWarm = 24;         // first stages of pass 1 that only look at chunk maxima
 // MODE_LISTS: [row][column half][kCap] keys, then one owner's 128 scores per warp
 constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
 // MODE_THETA: [row][3][kThetaPart] scores of column groups 1..3 for the final merge
@@ -718,17 +719,25 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 if (++tt == s_hi) tt = s_lo;
                 const float mb = chunk_max(x1);
                 if (MODE == MODE_THETA) {
-                    // every sampled score that beats this column group's current kThetaPart-th best
-                    if (ma > t8[kThetaPart - 1])
-                        for_each_ge(x0, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
-                            const float x = __uint_as_float(x0[j]);
-                            if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
-                        });
-                    if (mb > t8[kThetaPart - 1])
-                        for_each_ge(x1, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
-                            const float x = __uint_as_float(x1[j]);
-                            if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
-                        });
+                    if (t < kThetaWarm) {
+                        // warm-up: while the thresholds are still loose nearly every chunk passes; taking only the
+                        // chunk maxima (each of them a real score) tightens them at one insertion per chunk.  What
+                        // the other columns of those chunks might have contributed can only lower theta.
+                        if (ma > t8[kThetaPart - 1]) insert_desc(t8, ma);
+                        if (mb > t8[kThetaPart - 1]) insert_desc(t8, mb);
+                    } else {
+                        // every sampled score that beats this column group's current kThetaPart-th best
+                        if (ma > t8[kThetaPart - 1])
+                            for_each_ge(x0, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                                const float x = __uint_as_float(x0[j]);
+                                if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
+                            });
+                        if (mb > t8[kThetaPart - 1])
+                            for_each_ge(x1, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                                const float x = __uint_as_float(x1[j]);
+                                if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
+                            });
+                    }
                 } else {
                     if (ma >= tau)
                         for_each_ge(x0, tau, [&](int j) {
