@@ -92,6 +92,8 @@ int fwav_ctx_destroy(fwav_ctx *ctx) {
     if (ctx->d_transient) cudaFree(ctx->d_transient);
     if (ctx->d_w) cudaFree(ctx->d_w);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FWAV_OK;
@@ -307,12 +309,25 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, 
     FWAV_CUDA(ctx, cudaMemcpyAsync(d_signal, h_signal, sizeof(float) * (size_t)n_samples, cudaMemcpyHostToDevice, st));
     if (n_ranges)
         FWAV_CUDA(ctx, cudaMemcpyAsync(d_ranges, h_ranges, sizeof(float) * nr * N, cudaMemcpyHostToDevice, st));
+    // Build the tables first; the domain table (the .fwav payload, the largest transfer of the call) then travels
+    // to the host on the copy stream while the search runs on the compute stream.
+    if ((rc = fwav_launch_domains(ctx, d_signal, n_samples, tile_size, N, ds, d_domains, st))) return rc;
+    if (h_domains) {
+        if (!ctx->copy_stream) FWAV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        if (!ctx->copy_event) FWAV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+        FWAV_CUDA(ctx, cudaEventRecord(ctx->copy_event, st));
+        FWAV_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+        FWAV_CUDA(ctx, cudaMemcpyAsync(h_domains, d_domains, sizeof(float) * (size_t)n_dom * N, cudaMemcpyDeviceToHost,
+                                       ctx->copy_stream));
+    }
+    if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return rc;
     rc = fwav_compress_device(ctx, d_signal, n_samples, d_ranges, n_ranges, 0, tile_size, emb_dim, top_k,
-                              energy_thresh, fast_mode, query_mode, 1, d_domains, d_emb, d_idx, d_s, d_o,
+                              energy_thresh, fast_mode, query_mode, 0, d_domains, d_emb, d_idx, d_s, d_o,
                               d_sym, d_err, st);
-    if (rc) return rc;
-    if (h_domains)
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_domains, d_domains, sizeof(float) * (size_t)n_dom * N, cudaMemcpyDeviceToHost, st));
+    if (rc) {
+        if (h_domains) cudaStreamSynchronize(ctx->copy_stream);
+        return rc;
+    }
     if (n_ranges) {
         FWAV_CUDA(ctx, cudaMemcpyAsync(h_idx, d_idx, nr * 4, cudaMemcpyDeviceToHost, st));
         FWAV_CUDA(ctx, cudaMemcpyAsync(h_s, d_s, nr * 4, cudaMemcpyDeviceToHost, st));
@@ -321,6 +336,7 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, 
         FWAV_CUDA(ctx, cudaMemcpyAsync(h_sym, d_sym, nr, cudaMemcpyDeviceToHost, st));
     }
     FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_domains) FWAV_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return FWAV_OK;
 }
 

@@ -15,6 +15,8 @@ struct fwav_ctx {
     int device = 0;
     int num_sms = kNumSMsB200;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-buffer entry points: downloads that overlap the compute stream
+    cudaEvent_t copy_event = nullptr;
     char err[512] = {0};
     int search_impl = FWAV_SEARCH_AUTO;
     int64_t launches = 0;
