@@ -68,7 +68,7 @@ __device__ __forceinline__ void embed_row_static(const float (&x)[N], const Tabl
 }
 
 template <int N, int HALF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, N <= 16 ? 4 : 2)      // 12 warps per SM were not enough to hide the DFMA chains
 embed_static_kernel(const float *__restrict__ rows, long long n_rows, float *__restrict__ emb,
                     const __grid_constant__ TablesP<N, HALF> T) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;
