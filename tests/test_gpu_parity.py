@@ -438,6 +438,48 @@ def test_search_paths_agree(ctx, monkeypatch):
                   f"{ctx.search_fallbacks() - before} queries went to the exact list kernel")
 
 
+@pytest.mark.parametrize("n_q,top_k,frac_active,mode", [(1, 1, 1.0, None), (129, 7, 1.0, None), (777, 32, 0.5, None),
+                                                       (777, 32, 0.5, "precise"), (1500, 64, 0.9, None),
+                                                       (1500, 64, 0.9, "precise")])
+def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_active, mode):
+    """Random unit-norm two-head embeddings, a table size that is not a multiple of anything, query counts around
+    the 128-row tile, small and large K, the collect pass on the hi*hi term alone (what the probe picks here) and
+    forced onto the full fp16 split (FWAV_UMMA_MODE=precise): the tensor-core search must equal the FFMA kernel,
+    candidates and scores."""
+    if mode:
+        monkeypatch.setenv("FWAV_UMMA_MODE", mode)
+    else:
+        monkeypatch.delenv("FWAV_UMMA_MODE", raising=False)
+    ED = 16
+    n_d = (1 << 16) + 3
+    rng = np.random.default_rng(100 + n_q)
+    e = rng.standard_normal((n_d, ED)).astype(np.float32)
+    for h in (slice(0, 8), slice(8, 16)):
+        e[:, h] /= np.linalg.norm(e[:, h], axis=1, keepdims=True)
+    e[5::97] = e[4::97][: len(e[5::97])]                  # exact duplicates: ties broken by index
+    q = e[rng.choice(n_d, n_q, replace=False)] if n_q > 1 else e[:1]
+    q = np.ascontiguousarray(q + (rng.standard_normal(q.shape) * 0.05).astype(np.float32))
+    mask = rng.random(n_q) < frac_active
+    d_e, d_q, d_act = ctx.upload(e), ctx.upload(q), ctx.upload(mask.astype(np.uint8))
+    out = {}
+    for impl in IMPLS:
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * top_k * 4), ctx.alloc(n_q * top_k * 4)
+        try:
+            ctx.topk(d_q.ptr, n_q, d_e.ptr, n_d, ED, top_k, d_act.ptr, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32))
+    assert np.array_equal(out["umma"][0], out["ffma"][0])
+    assert np.array_equal(bits(out["umma"][1][mask]), bits(out["ffma"][1][mask]))
+    assert (out["umma"][0][~mask] == -1).all()
+    # and against a float64 brute force on a few rows: every returned score is within rounding of the true top-k
+    for i in np.flatnonzero(mask)[:5]:
+        sc = e.astype(np.float64) @ q[i].astype(np.float64)
+        kth = np.sort(sc)[-top_k]
+        assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
+
+
 def test_decode_properties(ctx):
     """Full-size-style checks that need no oracle: stored-s one-shot limit, idempotence."""
     rng = np.random.default_rng(1)
