@@ -45,7 +45,7 @@ typedef enum fwav_status {
 typedef enum fwav_search_impl {
     FWAV_SEARCH_AUTO = 0,  /* tensor-core path when the shape allows it */
     FWAV_SEARCH_FFMA = 1,  /* FP32 FFMA warp-select kernel */
-    FWAV_SEARCH_UMMA = 2   /* tcgen05 3xTF32 kernel + exact FP32 re-score */
+    FWAV_SEARCH_UMMA = 2   /* tcgen05 split-fp16 kernels (sampled threshold, collect, exact FP32 finalize; list kernel) */
 } fwav_search_impl;
 
 const char *fwav_version(void);
