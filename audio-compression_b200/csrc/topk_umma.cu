@@ -865,6 +865,7 @@ constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core scor
 // 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
 constexpr float kHiOnlySlack = 2e-3f;
 constexpr int kFinWarps = 4;
+constexpr int kFinRegs = 10;           // candidates per lane the register path of finalize_kernel holds (320 per query)
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
 #pragma unroll
@@ -902,42 +903,89 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
     overflow = !ok;
     int n_sel = 0;
     float last = -INFINITY;
-    if (ok) {
-        float qv[ED];
+    const int want = (long long)top_k < n_d ? top_k : (int)n_d;
+    // canonical score of candidate `id` as a key (0: a padded column past the end of the table)
+    float qv[ED];
+#pragma unroll
+    for (int k = 0; k < ED; k += 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(Q + q * ED + k));
+        qv[k] = f.x; qv[k + 1] = f.y; qv[k + 2] = f.z; qv[k + 3] = f.w;
+    }
+    auto key_of = [&](int id) -> unsigned long long {
+        if (id >= n_d) return 0ull;
+        float ev[ED];
 #pragma unroll
         for (int k = 0; k < ED; k += 4) {
-            const float4 f = __ldg(reinterpret_cast<const float4 *>(Q + q * ED + k));
-            qv[k] = f.x; qv[k + 1] = f.y; qv[k + 2] = f.z; qv[k + 3] = f.w;
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
+            ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
         }
+        return make_key(fwm::score_chain(qv, ev, ED), id);
+    };
+    if (ok && c <= 32 * kFinRegs) {
+        // the usual case: at most kFinRegs candidates per lane, kept in registers.  Every lane sorts its own keys
+        // (descending); a round is then a warp maximum over the lanes' heads and one pop.
+        unsigned long long k[kFinRegs];
+#pragma unroll
+        for (int j = 0; j < kFinRegs; ++j) k[j] = 0ull;
+        {
+            int off = 0;
+            for (int p = 0; p < parts; ++p) {          // candidate number g of the query = part p, entry g - off
+                const int cn = ccount[q * parts + p];
+                const int32_t *b = cbuf + (q * parts + p) * (long long)cap;
+#pragma unroll
+                for (int j = 0; j < kFinRegs; ++j) {
+                    const int g = lane + 32 * j;
+                    if (g >= off && g < off + cn) k[j] = key_of(b[g - off]);
+                }
+                off += cn;
+            }
+        }
+        // odd-even transposition sort of kFinRegs keys (descending)
+#pragma unroll
+        for (int pass = 0; pass < kFinRegs; ++pass) {
+#pragma unroll
+            for (int j = pass & 1; j + 1 < kFinRegs; j += 2) {
+                const unsigned long long hi = k[j] > k[j + 1] ? k[j] : k[j + 1], lo = k[j] > k[j + 1] ? k[j + 1] : k[j];
+                k[j] = hi;
+                k[j + 1] = lo;
+            }
+        }
+        for (int r = 0; r < want; ++r) {
+            const unsigned long long best = warp_max_u64(k[0]);
+            if (best == 0ull) break;
+            if (k[0] == best) {                        // keys are unique: exactly one lane pops
+#pragma unroll
+                for (int j = 0; j + 1 < kFinRegs; ++j) k[j] = k[j + 1];
+                k[kFinRegs - 1] = 0ull;
+            }
+            if (lane == 0) {
+                cand[q * top_k + r] = (int)(0xFFFFFFFFu - (uint32_t)best);
+                if (scores) scores[q * top_k + r] = unorder_bits((uint32_t)(best >> 32));
+            }
+            last = unorder_bits((uint32_t)(best >> 32));
+            ++n_sel;
+        }
+        ok = n_sel == want && last >= theta[q] + slack;
+        for (int i = want + lane; i < top_k; i += 32) {      // table smaller than top_k: pad like the reference
+            cand[q * top_k + i] = -1;
+            if (scores) scores[q * top_k + i] = -INFINITY;
+        }
+    } else if (ok) {
         int off = 0;
         for (int p = 0; p < parts; ++p) {
             const int cn = ccount[q * parts + p];
             const int32_t *b = cbuf + (q * parts + p) * (long long)cap;
-            for (int i = lane; i < cn; i += 32) {
-                const int id = b[i];
-                unsigned long long key = 0ull;                 // below every real key: padded columns
-                if (id < n_d) {
-                    float ev[ED];
-#pragma unroll
-                    for (int k = 0; k < ED; k += 4) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
-                        ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
-                    }
-                    key = make_key(fwm::score_chain(qv, ev, ED), id);
-                }
-                keys[off + i] = key;
-            }
+            for (int i = lane; i < cn; i += 32) keys[off + i] = key_of(b[i]);
             off += cn;
         }
         __syncwarp();
         // top_k rounds of "largest key below the previous one"
         unsigned long long prev = ~0ull;
-        const int want = (long long)top_k < n_d ? top_k : (int)n_d;
         for (int r = 0; r < want; ++r) {
             unsigned long long best = 0ull;
             for (int i = lane; i < c; i += 32) {
-                const unsigned long long k = keys[i];
-                if (k < prev && k > best) best = k;
+                const unsigned long long kk = keys[i];
+                if (kk < prev && kk > best) best = kk;
             }
             best = warp_max_u64(best);
             if (best == 0ull) break;
