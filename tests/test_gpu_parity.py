@@ -480,6 +480,57 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
 
 
+def test_config2_full_size_sample(ctx):
+    """BASELINE.json config 2 at FULL size (180 s / 44.1 kHz, 496 125 ranges x 1 983 477 domains) through the
+    host-buffer C ABI; a seeded sample of ranges is checked against the oracle: brute-force float32 search over the
+    whole table + the reference's affine match, with the north star's tie rules; then encode -> decode round trip
+    properties on the full result (one-shot limit of the damped decoder, idempotent second decode)."""
+    from fwav_b200 import _lib, synth
+    from fwav_b200.prestep import frame_ranges
+    sig, rate, tile, K = synth.make("c2", 1.0)
+    N, ds = _lib.geometry(tile)
+    ranges, original_len = frame_ranges(sig, N, 1e-4)
+    res = ctx.compress_host(sig, ranges, tile, 16, K, 1e-4, True, 0)
+    doms = res["domains"]
+    n_d, n_r = len(doms), len(ranges)
+    assert (n_r, n_d) == (496125, 1983477)
+    # domains: bit-exact on a strided sample of rows
+    want_dom = O.build_domains(sig[: 4096 + 4 * 4000], tile, N, ds)
+    assert np.array_equal(bits(doms[:len(want_dom)]), bits(want_dom))
+    embs = O.embed_rows(doms, 16, fast_norm=True).astype(np.float32)
+    rng = np.random.default_rng(7)
+    sample = np.sort(rng.choice(n_r, 96, replace=False))
+    n_tie = 0
+    for i in sample:
+        if O.is_pruned(ranges[i], 1e-4):
+            assert res["idx"][i] == 0 and np.isinf(res["err"][i]) and res["s"][i] == 0 and res["o"][i] == 0
+            continue
+        sc = embs @ embs[i]                                   # the reference's aliasing: q_i = E[i]
+        order = np.argsort(-sc, kind="stable")[:K + 8]
+        kth, nxt = sc[order[K - 1]], sc[order[K]]
+        cand = order[:K][None, :].astype(np.int32)
+        w = O.affine_match(ranges[i:i + 1], cand, doms, want_all=True)
+        same = res["idx"][i] == w["idx"][0] and res["sym"][i] == w["sym"][0]
+        if not same:
+            e = np.sort(w["all_err"][0])
+            near = abs(e[1] - e[0]) <= 1e-6 * max(abs(e[0]), 1e-30)
+            assert near or (kth - nxt) <= SCORE_TOL, (i, res["idx"][i], w["idx"][0], kth - nxt)
+            n_tie += 1
+            continue
+        assert abs(res["s"][i] - w["s"][0]) <= 1e-5 * abs(w["s"][0]) + 1e-30
+        assert abs(res["o"][i] - w["o"][0]) <= 1e-5 * abs(w["o"][0]) + 1e-30
+    print(f"config 2 full size: {len(sample)} sampled ranges, {n_tie} excused by a tie rule")
+    # decode properties at full size
+    rec1, it1, _ = ctx.decode_host(doms, res["idx"], res["s"], res["o"], res["sym"], N, iterations=8,
+                                   convergence_eps=1e-3, s_damping=0.0)
+    rec2, it2, _ = ctx.decode_host(doms, res["idx"], res["s"], res["o"], res["sym"], N, iterations=8,
+                                   convergence_eps=1e-3, s_damping=0.0)
+    assert it1 == it2 and np.array_equal(bits(rec1), bits(rec2))                  # deterministic
+    assert np.array_equal(bits(rec1), bits(np.repeat(res["o"], N)))               # F8: default decode == broadcast(o)
+    snr = O.compute_snr(sig[:original_len], rec1[:original_len])
+    assert np.isfinite(snr)
+
+
 def test_decode_properties(ctx):
     """Full-size-style checks that need no oracle: stored-s one-shot limit, idempotence."""
     rng = np.random.default_rng(1)
