@@ -109,6 +109,7 @@ struct ScanArgs {
     int32_t *cand;             // MODE_LISTS out
     float *scores;             // MODE_LISTS out (optional)
     float *theta;              // MODE_THETA out, MODE_COLLECT in
+    int theta_rank;            // MODE_THETA: which of the merged best sampled scores becomes theta (16 .. 24)
     float *theta_hi;           // MODE_THETA out: the (top_k / 16)-th best sampled score (about the top_k-th of the table)
     int32_t *cbuf;             // MODE_COLLECT out: [query][split][column group][cap] domain indices
     int *ccount;               // MODE_COLLECT out: [query][split][column group] how many passed (may exceed cap)
@@ -765,14 +766,20 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (half == 0 && q < n_q) {
-                float tm[kTheta];
+                constexpr int kMerged = 4 * kThetaPart;          // all four groups' lists, merged and sorted
+                float tm[kMerged];
 #pragma unroll
-                for (int i = 0; i < kTheta; ++i) tm[i] = i < kThetaPart ? t8[i] : (live ? -INFINITY : INFINITY);
+                for (int i = 0; i < kMerged; ++i) tm[i] = i < kThetaPart ? t8[i] : (live ? -INFINITY : INFINITY);
                 for (int i = 0; i < 3 * kThetaPart; ++i) {
                     const float x = th[(row0 + lane) * 3 * kThetaPart + i];
-                    if (x > tm[kTheta - 1]) insert_desc(tm, x);
+                    if (x > tm[kMerged - 1]) insert_desc(tm, x);
                 }
-                a.theta[q] = tm[kTheta - 1];      // +inf for pruned rows, -inf if the sample was too small
+                // theta = the theta_rank-th best sampled score (16th for top_k <= 32: ~256 domains reach it;
+                // 24th for top_k <= 64: ~384).  +inf for pruned rows, -inf if the sample was too small.
+                float tsel = tm[kTheta - 1];
+#pragma unroll
+                for (int i = kTheta; i < kMerged; ++i) tsel = (i == a.theta_rank - 1) ? tm[i] : tsel;
+                a.theta[q] = tsel;
                 int hi_rank = top_k / 16 - 1;
                 hi_rank = hi_rank < 0 ? 0 : hi_rank > kTheta - 1 ? kTheta - 1 : hi_rank;
                 float th = tm[0];
@@ -1106,6 +1113,7 @@ bool fwav_topk_umma_supported(int emb_dim, int top_k, int64_t n_q, int64_t n_d) 
 namespace {
 
 constexpr int kCollectCap = 192;              // candidate indices kept per (query, column group of 64)
+constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
@@ -1228,7 +1236,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 4) * sizeof(float), (void **)&d_theta))) return rc;
     float *d_theta_hi = d_theta + n_q;
     int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
-    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * kCollectCap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
+    const int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * collect_cap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
     int *d_fail_count = d_fail + n_q;
@@ -1243,7 +1252,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.q_tiles = d_qt + (q0 / kQTile) * (kTileBytes / 16);
         a.e_tiles = d_et; a.Q = d_q + q0 * ED; a.E = d_emb; a.n_q = nq; a.n_d = n_d;
         a.n_stages = (int)n_stages; a.top_k = top_k; a.active = d_active ? d_active + q0 : nullptr;
-        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = kCollectCap; a.dbg = dbg;
+        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.theta_rank = top_k > 32 ? 24 : kTheta; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = collect_cap; a.dbg = dbg;
         a.n_split = 1;
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
         // pass 1 keeps the full split: on data whose scores crowd together a threshold that is off by the hi*hi
@@ -1286,7 +1295,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             }
         }
         const long long main_q = tail_groups ? main_groups * kQTile : nq;
-        const int tail_cap = kCollectCap / 2;      // a split sees 1/tail_split of the table: ~256 / (4 * tail_split) hits per part expected
+        const int tail_cap = collect_cap / 2;      // a split sees 1/tail_split of the table: ~256 / (4 * tail_split) hits per part expected
         ScanArgs at = a;
         if (tail_groups) {
             int32_t *d_tbuf = nullptr;

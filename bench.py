@@ -290,7 +290,10 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)]  # noqa: E731
-    for _ in range(max(args.warmup, 3)):
+    # the contract's W >= 3 holds for the metric's configuration; the hour-scale extra workloads (c3, c4: tens of
+    # seconds per pass) may be run with fewer warm-up passes
+    n_warm = max(args.warmup, 3) if WORKLOAD == "c2" else max(args.warmup, 1)
+    for _ in range(n_warm):
         step(mk())
     barrier()
     launches0 = ctx.launch_count()
@@ -445,7 +448,7 @@ def run_ours(args):
 
     line = {
         "metric": "ranges_matched_per_s", "value": value, "unit": "ranges/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(w, args.scale), "n_samples": n, "n_ranges": n_r,
