@@ -20,6 +20,7 @@ struct fwav_ctx {
     char err[512] = {0};
     int search_impl = FWAV_SEARCH_AUTO;
     int64_t launches = 0;
+    int64_t umma_ffma_queries = 0;       // of those (top_k > 32), queries that also failed the second tensor-core chance
     int64_t umma_fallback_queries = 0;   // queries the fast search path handed to the exact list kernel
     // CUDA events around the kernels of the last tensor-core search call (fwav_ctx_search_timings)
     static constexpr int kSearchPhases = 5;          // pack, threshold pass, collect pass, finalize, list kernel

@@ -1039,6 +1039,10 @@ __global__ void gather_rows_kernel(const float *__restrict__ Q, const int *__res
     const int r = i / (ED / 4), k = i % (ED / 4);
     reinterpret_cast<float4 *>(out)[i] = __ldg(reinterpret_cast<const float4 *>(Q + (long long)list[r] * ED) + k);
 }
+__global__ void gather_f32_kernel(const float *__restrict__ src, const int *__restrict__ list, int n, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[list[i]];
+}
 __global__ void scatter_cand_kernel(const int32_t *__restrict__ src, const float *__restrict__ src_scores,
                                     const int *__restrict__ list, int n, int top_k, int32_t *__restrict__ cand,
                                     float *__restrict__ scores) {
@@ -1236,7 +1240,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 4) * sizeof(float), (void **)&d_theta))) return rc;
     float *d_theta_hi = d_theta + n_q;
     int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
-    const int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
+    int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
+    if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
+        const int v = atoi(cap_env);
+        if (v >= 2 && v <= collect_cap) collect_cap = v & ~1;
+    }
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * collect_cap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
@@ -1366,26 +1374,87 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         if (n_fail > 0 && dbg) FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));   // profiling modes: wrong anyway
         if (n_fail > 0 && !dbg) {
             const long long fp = (n_fail + kQPair - 1) / kQPair;
-            float *d_fq = nullptr, *d_fs = nullptr;
-            uint4 *d_fqt = nullptr;
-            int32_t *d_fc = nullptr;
             unsigned char *blk = nullptr;
             const size_t sz_q = (size_t)fp * kQPair * ED * sizeof(float), sz_t = (size_t)fp * 2 * kTileBytes,
-                         sz_c = (size_t)n_fail * top_k * sizeof(int32_t);
-            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, sz_q + sz_t + 2 * sz_c + 64, (void **)&blk))) return rc;
-            d_fq = reinterpret_cast<float *>(blk);
-            d_fqt = reinterpret_cast<uint4 *>(blk + sz_q);
-            d_fc = reinterpret_cast<int32_t *>(blk + sz_q + sz_t);
-            d_fs = reinterpret_cast<float *>(blk + sz_q + sz_t + sz_c);
+                         sz_c = (((size_t)n_fail * top_k * sizeof(int32_t)) + 255) & ~(size_t)255,
+                         sz_n = (((size_t)n_fail + 4) * sizeof(int) + 255) & ~(size_t)255;
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, 2 * sz_q + sz_t + 4 * sz_c + 2 * sz_n, (void **)&blk))) return rc;
+            float *d_fq = reinterpret_cast<float *>(blk);
+            uint4 *d_fqt = reinterpret_cast<uint4 *>(blk + sz_q);
+            int32_t *d_fc = reinterpret_cast<int32_t *>(blk + sz_q + sz_t);
+            float *d_fs = reinterpret_cast<float *>(blk + sz_q + sz_t + sz_c);
+            float *d_ftheta = reinterpret_cast<float *>(blk + sz_q + sz_t + 2 * sz_c);
+            int *d_fail2 = reinterpret_cast<int *>(blk + sz_q + sz_t + 2 * sz_c + sz_n);
+            float *d_fq2 = reinterpret_cast<float *>(blk + sz_q + sz_t + 2 * sz_c + 2 * sz_n);
+            int32_t *d_fc2 = reinterpret_cast<int32_t *>(blk + 2 * sz_q + sz_t + 2 * sz_c + 2 * sz_n);
+            float *d_fs2 = reinterpret_cast<float *>(blk + 2 * sz_q + sz_t + 3 * sz_c + 2 * sz_n);
             gather_rows_kernel<<<(n_fail * (ED / 4) + 255) / 256, 256, 0, st>>>(d_q + q0 * ED, d_fail, n_fail, d_fq);
             FWAV_LAUNCH_CHECK(ctx);
             pack_f16_tiles_kernel<<<grid_for(ctx, fp * 2 * kDTile * 2), 256, 0, st>>>(d_fq, n_fail, fp * 2, d_fqt, 1);
             FWAV_LAUNCH_CHECK(ctx);
-            if (top_k <= 32)
+            if (top_k <= 32) {
                 rc = launch_lists(ctx, d_fqt, d_et, d_fq, d_emb, n_fail, n_d, (int)n_stages, top_k, nullptr, d_fc, d_fs, dbg, st);
-            else
-                rc = fwav_launch_topk_ffma(ctx, d_fq, n_fail, d_emb, n_d, ED, top_k, nullptr, d_fc, d_fs, st);
-            if (rc) return rc;
+                if (rc) return rc;
+            } else {
+                // No list kernel for top_k > 32, and the FFMA scan costs milliseconds per query on a large table.
+                // Second chance on the tensor cores first: the failed queries alone, same thresholds, full split
+                // (slack 4e-6 instead of 2e-3), the table split between up to eight CTAs per 128 queries, each
+                // with its own candidate buffers: many times the room per query.  What fails again goes to FFMA.
+                const long long fg = (n_fail + kQTile - 1) / kQTile;
+                long long rs = ctx->num_sms / fg;
+                if (rs > 8) rs = 8;
+                if (rs > n_stages / 8) rs = n_stages / 8;
+                if (rs < 1) rs = 1;
+                const bool retry = single && (hi_only || rs >= 2) && !(mode_env && !strcmp(mode_env, "noretry"));
+                int n_fail2 = n_fail;
+                const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
+                if (retry) {
+                    const int rcap = rs >= 2 ? collect_cap / 2 : collect_cap;
+                    int32_t *d_rbuf = nullptr;
+                    const size_t nb = (size_t)n_fail * rs * 4 * rcap * sizeof(int32_t), nc = (size_t)n_fail * rs * 4 * sizeof(int);
+                    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_rbuf))) return rc;
+                    gather_f32_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>(d_theta + q0, d_fail, n_fail, d_ftheta);
+                    FWAV_LAUNCH_CHECK(ctx);
+                    FWAV_CUDA(ctx, cudaMemsetAsync(d_fail2 + n_fail, 0, 4 * sizeof(int), st));
+                    ScanArgs ar = a;
+                    ar.q_tiles = d_fqt; ar.Q = d_fq; ar.n_q = n_fail; ar.active = nullptr; ar.theta = d_ftheta;
+                    ar.n_split = (int)rs; ar.cbuf = d_rbuf; ar.cap = rcap;
+                    ar.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_rbuf) + nb);
+                    if ((rc = launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st))) return rc;
+                    const int parts = 4 * (int)rs;
+                    const size_t fin_smem = (size_t)kFinWarps * parts * rcap * sizeof(unsigned long long);
+                    if (fin_smem > 48 * 1024)
+                        FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+                    finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
+                        d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, kScoreSlack,
+                        d_fc, d_fs, d_fail2, d_fail2 + n_fail);
+                    FWAV_LAUNCH_CHECK(ctx);
+                    int h_fail2[4] = {0, 0, 0, 0};
+                    FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail2, d_fail2 + n_fail, sizeof h_fail2, cudaMemcpyDeviceToHost, st));
+                    FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+                    n_fail2 = h_fail2[0];
+                    d_list2 = d_fail2;
+                    if (getenv("FWAV_UMMA_VERBOSE"))
+                        fprintf(stderr, "[fwav] search batch at %lld: second chance (full split, table split %lld ways): %d of %d fail again (overflow %d, short %d, boundary %d)\n",
+                                q0, rs, n_fail2, n_fail, h_fail2[1], h_fail2[2], h_fail2[3]);
+                }
+                ctx->umma_ffma_queries += n_fail2;
+                if (n_fail2 > 0) {
+                    const float *d_in = d_fq;
+                    if (d_list2) {
+                        gather_rows_kernel<<<(n_fail2 * (ED / 4) + 255) / 256, 256, 0, st>>>(d_fq, d_list2, n_fail2, d_fq2);
+                        FWAV_LAUNCH_CHECK(ctx);
+                        d_in = d_fq2;
+                    }
+                    if ((rc = fwav_launch_topk_ffma(ctx, d_in, n_fail2, d_emb, n_d, ED, top_k, nullptr, d_list2 ? d_fc2 : d_fc,
+                                                    d_list2 ? d_fs2 : d_fs, st)))
+                        return rc;
+                    if (d_list2) {
+                        scatter_cand_kernel<<<(n_fail2 * top_k + 255) / 256, 256, 0, st>>>(d_fc2, d_fs2, d_list2, n_fail2, top_k, d_fc, d_fs);
+                        FWAV_LAUNCH_CHECK(ctx);
+                    }
+                }
+            }
             scatter_cand_kernel<<<(n_fail * top_k + 255) / 256, 256, 0, st>>>(d_fc, d_fs, d_fail, n_fail, top_k,
                                                                                d_cand + q0 * top_k,
                                                                                d_scores ? d_scores + q0 * top_k : nullptr);

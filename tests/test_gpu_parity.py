@@ -423,6 +423,26 @@ def test_search_paths_agree(ctx, monkeypatch):
     g64, gs64 = run64("umma", 2000)
     assert np.array_equal(g64, w64) and np.array_equal(bits(gs64), bits(ws64))
     print(f"top_k=64, n_q=2000: equal to FFMA; {ctx.search_fallbacks() - before} queries went to the fallback")
+    # tiny candidate buffers force the failure routes: second chance on the tensor cores (full split, table
+    # split between CTAs), then the FFMA kernel for what fails again; with "noretry" straight to FFMA
+    for cap, mode in ((48, None), (16, None), (48, "noretry")):
+        monkeypatch.setenv("FWAV_UMMA_CAP", str(cap))
+        if mode:
+            monkeypatch.setenv("FWAV_UMMA_MODE", mode)
+        before = ctx.search_fallbacks()
+        set_impl(ctx, "umma")
+        d_cand, d_sc = ctx.alloc(2000 * K64 * 4), ctx.alloc(2000 * K64 * 4)
+        try:
+            ctx.topk(d_emb.ptr, 2000, d_emb.ptr, n_d, ED, K64, None, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+            monkeypatch.delenv("FWAV_UMMA_CAP")
+            monkeypatch.delenv("FWAV_UMMA_MODE", raising=False)
+        n_fb = ctx.search_fallbacks() - before
+        assert n_fb > 0, "the cap knob should have forced failures"
+        assert np.array_equal(d_cand.to_host((2000, K64), np.int32), w64), (cap, mode)
+        assert np.array_equal(bits(d_sc.to_host((2000, K64), np.float32)), bits(ws64)), (cap, mode)
+        print(f"top_k=64, cap={cap} mode={mode}: equal to FFMA; {n_fb} queries failed the first collect pass")
 
     for n_q in (5000, 300):          # 300 queries: two CTA pairs, so the list kernel splits the table
         mask = rng.random(n_q) > 0.2
