@@ -776,9 +776,9 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 }
                 // theta = the theta_rank-th best sampled score (16th for top_k <= 32: ~256 domains reach it;
                 // 24th for top_k <= 64: ~384).  +inf for pruned rows, -inf if the sample was too small.
-                float tsel = tm[kTheta - 1];
+                float tsel = tm[0];
 #pragma unroll
-                for (int i = kTheta; i < kMerged; ++i) tsel = (i == a.theta_rank - 1) ? tm[i] : tsel;
+                for (int i = 1; i < kMerged; ++i) tsel = (i == a.theta_rank - 1) ? tm[i] : tsel;
                 a.theta[q] = tsel;
                 int hi_rank = top_k / 16 - 1;
                 hi_rank = hi_rank < 0 ? 0 : hi_rank > kTheta - 1 ? kTheta - 1 : hi_rank;
@@ -885,9 +885,10 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x)
 
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
-                const uint8_t *__restrict__ active, const float *__restrict__ theta, const int32_t *__restrict__ cbuf,
+                const uint8_t *__restrict__ active, const float *theta, const int32_t *__restrict__ cbuf,
                 const int *__restrict__ ccount, int cap, int parts, int q_index0, float slack, int32_t *__restrict__ cand,
-                float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count) {
+                float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count,
+                float *theta_retry /* may alias theta: a failed query's threshold for the second pass */) {
     extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][parts * cap]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * kFinWarps + warp;
@@ -1013,6 +1014,10 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
     if (!ok && lane == 0) {
         fail_list[atomicAdd(fail_count, 1)] = (int)q + q_index0;
         atomicAdd(fail_count + (overflow ? 1 : n_sel < top_k ? 2 : 3), 1);      // diagnostics: why
+        // "boundary": enough candidates, but the last one sits within the slack of theta, so a better one may have
+        // been filtered out.  Every domain that beats `last` scores at least last - kScoreSlack on the tensor
+        // cores with the full split: a second collect pass with this threshold finds them all and verifies.
+        if (theta_retry && !overflow && n_sel == want && want > 0) theta_retry[q] = fminf(theta[q], last - 2.0f * kScoreSlack);
     }
 }
 
@@ -1250,6 +1255,14 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
     int *d_fail_count = d_fail + n_q;
     FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
+    // 16 x rank candidates expected per query.  P(fewer than top_k reach theta) = P(Bin(top_k, 1/16) >= rank):
+    // 1e-11 for (32, 16), 5e-8 for (64, 18).  A lower rank for top_k <= 32 leaves too little room between the
+    // top_k-th score and theta for the hi*hi-only collect pass (config 2 at rank 12: 1 % of the queries under 4e-3).
+    int theta_rank = top_k > 32 ? 18 : kTheta;
+    if (const char *rank_env = getenv("FWAV_UMMA_RANK")) {     // tuning knob: 16 x rank candidates expected per query
+        const int v = atoi(rank_env);
+        if (v >= 1 && v <= 4 * kThetaPart) theta_rank = v;
+    }
     int slot = 0;
     for (long long q0 = 0; q0 < n_q; q0 += batch, ++slot) {
         if (slot > 0 && (rc = mark(ctx, slot, 0, st))) return rc;      // later batches: nothing to pack
@@ -1260,7 +1273,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.q_tiles = d_qt + (q0 / kQTile) * (kTileBytes / 16);
         a.e_tiles = d_et; a.Q = d_q + q0 * ED; a.E = d_emb; a.n_q = nq; a.n_d = n_d;
         a.n_stages = (int)n_stages; a.top_k = top_k; a.active = d_active ? d_active + q0 : nullptr;
-        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.theta_rank = top_k > 32 ? 24 : kTheta; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = collect_cap; a.dbg = dbg;
+        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.theta_rank = theta_rank; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = collect_cap; a.dbg = dbg;
         a.n_split = 1;
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
         // pass 1 keeps the full split: on data whose scores crowd together a threshold that is off by the hi*hi
@@ -1358,7 +1371,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                               fin_smem, st>>>(
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
                 hi_only ? kHiOnlySlack : kScoreSlack, d_cand + (q0 + qoff) * top_k,
-                d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count);
+                d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
+                top_k > 32 ? d_theta + q0 + qoff : nullptr);
             FWAV_LAUNCH_CHECK(ctx);
         }
         if ((rc = mark(ctx, slot, 4, st))) return rc;
@@ -1427,7 +1441,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
                     finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
                         d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, kScoreSlack,
-                        d_fc, d_fs, d_fail2, d_fail2 + n_fail);
+                        d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr);
                     FWAV_LAUNCH_CHECK(ctx);
                     int h_fail2[4] = {0, 0, 0, 0};
                     FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail2, d_fail2 + n_fail, sizeof h_fail2, cudaMemcpyDeviceToHost, st));

@@ -28,6 +28,6 @@ for r in range(reps + 1):
     e1.record(); torch.cuda.synchronize()
     if r: ms.append(e0.elapsed_time(e1))
 pairs = float(n_q) * n_d
-print(json.dumps(dict(fallbacks=ctx.search_fallbacks(), reps=reps + 1, impl=impl, dbg=os.environ.get("FWAV_UMMA_DEBUG", "0"), scale=scale, n_q=n_q, n_d=n_d,
+print(json.dumps(dict(fallbacks=ctx.search_fallbacks(), phases={k: round(v, 3) for k, v in ctx.search_timings().items()}, rank=os.environ.get('FWAV_UMMA_RANK', 'default'), reps=reps + 1, impl=impl, dbg=os.environ.get("FWAV_UMMA_DEBUG", "0"), scale=scale, n_q=n_q, n_d=n_d,
                       ms=float(np.mean(ms)), gpairs_per_s=pairs / np.mean(ms) / 1e6,
                       cycles_per_tilestep_per_sm=np.mean(ms) * 1e-3 * 1.965e9 / (((n_q + 255) // 256) * ((n_d + 127) // 128) / 148))))

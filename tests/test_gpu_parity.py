@@ -425,8 +425,10 @@ def test_search_paths_agree(ctx, monkeypatch):
     print(f"top_k=64, n_q=2000: equal to FFMA; {ctx.search_fallbacks() - before} queries went to the fallback")
     # tiny candidate buffers force the failure routes: second chance on the tensor cores (full split, table
     # split between CTAs), then the FFMA kernel for what fails again; with "noretry" straight to FFMA
-    for cap, mode in ((48, None), (16, None), (48, "noretry")):
+    for cap, mode, rank in ((48, None, None), (16, None, None), (48, "noretry", None), (320, None, 5)):
         monkeypatch.setenv("FWAV_UMMA_CAP", str(cap))
+        if rank:        # a threshold too high: "short" and "boundary" failures instead of overflows
+            monkeypatch.setenv("FWAV_UMMA_RANK", str(rank))
         if mode:
             monkeypatch.setenv("FWAV_UMMA_MODE", mode)
         before = ctx.search_fallbacks()
@@ -437,12 +439,13 @@ def test_search_paths_agree(ctx, monkeypatch):
         finally:
             set_impl(ctx, "auto")
             monkeypatch.delenv("FWAV_UMMA_CAP")
+            monkeypatch.delenv("FWAV_UMMA_RANK", raising=False)
             monkeypatch.delenv("FWAV_UMMA_MODE", raising=False)
         n_fb = ctx.search_fallbacks() - before
         assert n_fb > 0, "the cap knob should have forced failures"
         assert np.array_equal(d_cand.to_host((2000, K64), np.int32), w64), (cap, mode)
         assert np.array_equal(bits(d_sc.to_host((2000, K64), np.float32)), bits(ws64)), (cap, mode)
-        print(f"top_k=64, cap={cap} mode={mode}: equal to FFMA; {n_fb} queries failed the first collect pass")
+        print(f"top_k=64, cap={cap} mode={mode} rank={rank}: equal to FFMA; {n_fb} queries failed the first collect pass")
 
     for n_q in (5000, 300):          # 300 queries: two CTA pairs, so the list kernel splits the table
         mask = rng.random(n_q) > 0.2
