@@ -473,8 +473,19 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
 // CG: CTAs per tensor-core group.  2 = the pair described above (a domain tile is read once per 256 queries).
 // 1 = every CTA on its own (M = 128, the whole 256-domain stage in its shared memory, all barriers local: no relay,
 // no remote arrive, no multicast commit in the accumulator hand-over chain that bounds the streaming modes).
+#ifndef FWAV_ALT_SETS
+#define FWAV_ALT_SETS 1
+#endif
+
 template <int MODE, bool HI, int CG>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+    // hi*hi-only collect pass: the sixteen epilogue warps form two sets, one per TMEM buffer.  A set takes every
+    // other stage (128 columns per warp), so while one set waits for its tcgen05.ld the other one is reducing;
+    // with all warps on every stage they move in lockstep and the load time adds to the ALU time (collect pass of
+    // config 2: 73.0 -> 68.7 ms).  A set hands its buffer back only after its second pair of loads, which costs
+    // more than it gains when a stage takes three MMAs (threshold pass 7.8 -> 10.1 ms, full-split collect +3.5 %):
+    // those keep all warps on every stage.
+    constexpr bool kAlt = FWAV_ALT_SETS && MODE == MODE_COLLECT && HI;
     constexpr int kQGroup = kQTile * CG;                             // queries per tensor-core group
     constexpr uint32_t kStageBytes = stage_bytes(CG);                // B bytes per stage in this CTA's shared memory
     constexpr uint32_t kOffB = off_ring(MODE);
@@ -536,7 +547,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         // the leader's "stage has landed" barriers collect its own copy and the peer's relay
         const uint32_t n_land = (CG == 2 && cta_rank == 0) ? 2u : 1u;
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, n_land); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, CG * kEpi); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, CG * kEpi / (kAlt ? 2 : 1)); }
         mbar_init(bar_a, n_land);
         mbar_init(bar_a + 8, 1);
         mbar_init(bar_a + 16, 1);
@@ -654,7 +665,10 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         const long long q = q_base + row0 + lane;
         const bool live = q < n_q && (!active || active[q]) && !(dbg & 4);
         constexpr int kCols = kDStage / (kEpi / 4);       // columns per warp and stage
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
+        // two sets: `half` = set + 2 * (which 128 columns); the set's buffer never changes
+        const int set = half & 1, colhalf = half >> 1;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                (uint32_t)(kAlt ? set * kDStage + colhalf * 128 : half * kCols);
         // mode state
         float tau = live ? -INFINITY : INFINITY;                    // LISTS: running threshold; +inf: never a candidate
         unsigned long long *lists = rows + ((size_t)row0 * 2 + half) * kCap;     // row r of the warp: lists + r * 2 * kCap
@@ -698,6 +712,57 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 const float m2 = chunk_max(v[2]), m3 = chunk_max(v[3]);
                 const unsigned hits = (m0 > tau ? 1u : 0u) | (m1 > tau ? 2u : 0u) | (m2 > tau ? 4u : 0u) | (m3 > tau ? 8u : 0u);
                 if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
+            }
+        } else if (kAlt && !(dbg & 8)) {
+            uint32_t x0[32], x1[32];
+            int it = 0;
+            // one 32-column chunk with its maximum m: THETA keeps the group's best scores, COLLECT appends indices
+            auto look = [&](const uint32_t (&x)[32], float m, int col) {
+                if (MODE == MODE_THETA) {
+                    if (it < kThetaWarm / 2) {
+                        if (m > t8[kThetaPart - 1]) insert_desc(t8, m);      // warm-up: chunk maxima only (see below)
+                    } else if (m > t8[kThetaPart - 1]) {
+                        for_each_ge(x, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                            const float v = __uint_as_float(x[j]);
+                            if (v > t8[kThetaPart - 1]) insert_desc(t8, v);
+                        });
+                    }
+                } else if (m >= tau) {
+                    for_each_ge(x, tau, [&](int j) {
+                        if (cnt < a.cap) cbuf[cnt] = col + j;
+                        ++cnt;
+                    });
+                }
+            };
+            tt = t_first + set;
+            if (tt >= s_hi) tt -= n_visit;
+            const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tempty + 8 * set;
+            for (int t = set; t < n_visit; t += 2, ++it) {
+                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+                tc_fence_after();
+                tmem_ld32(t_lane, x0);
+                tmem_ld32(t_lane + 32, x1);
+                tmem_wait_ld2(x0, x1);
+                const int col0 = tt * kDStage + colhalf * 128;
+                tt += 2;
+                if (tt >= s_hi) tt -= n_visit;
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0);
+                    look(x1, mb, col0 + 32);
+                }
+                tmem_ld32(t_lane + 64, x0);
+                tmem_ld32(t_lane + 96, x1);
+                tmem_wait_ld2(x0, x1);
+                // the warp's share of the buffer has been read: hand it back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_remote(bar_e, 0); else mbar_arrive_local(bar_e); }
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0 + 64);
+                    look(x1, mb, col0 + 96);
+                }
             }
         } else if (!(dbg & 8)) {
             // Streaming epilogue: 64 columns per warp and stage, four warps per scheduler interleave their chains.
@@ -872,6 +937,7 @@ constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core scor
 // 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
 constexpr float kHiOnlySlack = 2e-3f;
 constexpr int kFinWarps = 4;
+constexpr int kFinKeys = 768;          // keys per query the shared-memory path of the first finalize holds (the second chance: all)
 constexpr int kFinRegs = 10;           // candidates per lane the register path of finalize_kernel holds (320 per query)
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
@@ -888,8 +954,8 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
                 const uint8_t *__restrict__ active, const float *theta, const int32_t *__restrict__ cbuf,
                 const int *__restrict__ ccount, int cap, int parts, int q_index0, float slack, int32_t *__restrict__ cand,
                 float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count,
-                float *theta_retry /* may alias theta: a failed query's threshold for the second pass */) {
-    extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][parts * cap]
+                float *theta_retry /* may alias theta: a failed query's threshold for the second pass */, int key_cap) {
+    extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][key_cap]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * kFinWarps + warp;
     if (q >= n_q) return;
@@ -900,7 +966,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         }
         return;
     }
-    unsigned long long *keys = fin_keys + (size_t)warp * parts * cap;
+    unsigned long long *keys = fin_keys + (size_t)warp * key_cap;
     int c = 0;
     bool ok = true, overflow = false;
     for (int p = 0; p < parts; ++p) {                  // parts = 4 column groups x table splits
@@ -908,6 +974,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         ok = ok && cn <= cap;
         c += cn;
     }
+    ok = ok && c <= key_cap;                           // more than the shared-memory path holds: treated as an overflow
     overflow = !ok;
     int n_sel = 0;
     float last = -INFINITY;
@@ -1121,7 +1188,7 @@ bool fwav_topk_umma_supported(int emb_dim, int top_k, int64_t n_q, int64_t n_d) 
 
 namespace {
 
-constexpr int kCollectCap = 192;              // candidate indices kept per (query, column group of 64)
+constexpr int kCollectCap = 256;              // candidate indices kept per (query, column group of 64)
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
@@ -1364,7 +1431,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const ScanArgs &ax = part ? at : a;
             const long long qoff = part ? main_q : 0;
             const int parts = 4 * ax.n_split;
-            const size_t fin_smem = (size_t)kFinWarps * parts * ax.cap * sizeof(unsigned long long);
+            const int key_cap = parts * ax.cap < kFinKeys ? parts * ax.cap : kFinKeys;
+            const size_t fin_smem = (size_t)kFinWarps * key_cap * sizeof(unsigned long long);
             if (fin_smem > 48 * 1024)
                 FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
             finalize_kernel<<<(unsigned)((ax.n_q + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
@@ -1372,7 +1440,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
                 hi_only ? kHiOnlySlack : kScoreSlack, d_cand + (q0 + qoff) * top_k,
                 d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
-                top_k > 32 ? d_theta + q0 + qoff : nullptr);
+                top_k > 32 ? d_theta + q0 + qoff : nullptr, key_cap);
             FWAV_LAUNCH_CHECK(ctx);
         }
         if ((rc = mark(ctx, slot, 4, st))) return rc;
@@ -1441,7 +1509,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
                     finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
                         d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, kScoreSlack,
-                        d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr);
+                        d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, parts * rcap);
                     FWAV_LAUNCH_CHECK(ctx);
                     int h_fail2[4] = {0, 0, 0, 0};
                     FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail2, d_fail2 + n_fail, sizeof h_fail2, cudaMemcpyDeviceToHost, st));
