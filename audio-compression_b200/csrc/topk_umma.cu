@@ -109,6 +109,7 @@ struct ScanArgs {
     int32_t *cand;             // MODE_LISTS out
     float *scores;             // MODE_LISTS out (optional)
     float *theta;              // MODE_THETA out, MODE_COLLECT in
+    int hi_rank;               // MODE_THETA: which sampled score estimates the top_k-th best of the table (top_k / stride)
     int theta_rank;            // MODE_THETA: which of the merged best sampled scores becomes theta (16 .. 24)
     float *theta_hi;           // MODE_THETA out: the (top_k / 16)-th best sampled score (about the top_k-th of the table)
     int32_t *cbuf;             // MODE_COLLECT out: [query][split][column group][cap] domain indices
@@ -845,7 +846,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 #pragma unroll
                 for (int i = 1; i < kMerged; ++i) tsel = (i == a.theta_rank - 1) ? tm[i] : tsel;
                 a.theta[q] = tsel;
-                int hi_rank = top_k / 16 - 1;
+                int hi_rank = a.hi_rank - 1;
                 hi_rank = hi_rank < 0 ? 0 : hi_rank > kTheta - 1 ? kTheta - 1 : hi_rank;
                 float th = tm[0];
 #pragma unroll
@@ -1297,11 +1298,18 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     // ---- fast path: sampled threshold, collect, finalize + verify, exact fallback for the failures ----
     // pass 1 scans a strided sample of the table (every 16th domain), packed like the table itself:
     // neighbouring domains are near-duplicates of each other, a strided sample is not
-    const long long n_samp = (n_d + kSampleStride - 1) / kSampleStride;
+    // top_k <= 32: every 32nd domain and the 8th best sampled score (256 candidates expected, like 16 x 16, at
+    // half the cost of pass 1: 7.75 -> 4.4 ms on config 2; the wider spread costs ~40 instead of ~1 second chances)
+    int sample_stride = top_k > 32 ? kSampleStride : 2 * kSampleStride;
+    if (const char *stride_env = getenv("FWAV_UMMA_STRIDE")) {     // tuning knob (with FWAV_UMMA_RANK: stride x rank candidates)
+        const int v = atoi(stride_env);
+        if (v >= 2 && v <= 256) sample_stride = v;
+    }
+    const long long n_samp = (n_d + sample_stride - 1) / sample_stride;
     const long long s_stages = (n_samp + kDStage - 1) / kDStage;
     uint4 *d_es = nullptr;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_MISC, (size_t)s_stages * 2 * kTileBytes, (void **)&d_es))) return rc;
-    pack_f16_tiles_kernel<<<grid_for(ctx, s_stages * 2 * kDTile * 2), 256, 0, st>>>(d_emb, n_d, s_stages * 2, d_es, kSampleStride);
+    pack_f16_tiles_kernel<<<grid_for(ctx, s_stages * 2 * kDTile * 2), 256, 0, st>>>(d_emb, n_d, s_stages * 2, d_es, sample_stride);
     FWAV_LAUNCH_CHECK(ctx);
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
@@ -1322,10 +1330,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_fail))) return rc;
     int *d_fail_count = d_fail + n_q;
     FWAV_CUDA(ctx, cudaMemsetAsync(d_fail_count, 0, 4 * sizeof(int), st));
-    // 16 x rank candidates expected per query.  P(fewer than top_k reach theta) = P(Bin(top_k, 1/16) >= rank):
-    // 1e-11 for (32, 16), 5e-8 for (64, 18).  A lower rank for top_k <= 32 leaves too little room between the
-    // top_k-th score and theta for the hi*hi-only collect pass (config 2 at rank 12: 1 % of the queries under 4e-3).
-    int theta_rank = top_k > 32 ? 18 : kTheta;
+    // stride x rank candidates expected per query.  P(fewer than top_k reach theta) = P(Bin(top_k, 1/stride) >= rank):
+    // 1e-5 for (32; 1/32, 8) -- a handful of second chances per half million queries -- and 5e-8 for (64; 1/16, 18).
+    // Fewer candidates do not pay for top_k <= 32: they leave too little room between the top_k-th score and theta
+    // for the hi*hi-only collect pass (config 2 at 16 x 12: 1 % of the queries under 4e-3).
+    int theta_rank = top_k > 32 ? 18 : kTheta / 2;
     if (const char *rank_env = getenv("FWAV_UMMA_RANK")) {     // tuning knob: 16 x rank candidates expected per query
         const int v = atoi(rank_env);
         if (v >= 1 && v <= 4 * kThetaPart) theta_rank = v;
@@ -1340,7 +1349,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         a.q_tiles = d_qt + (q0 / kQTile) * (kTileBytes / 16);
         a.e_tiles = d_et; a.Q = d_q + q0 * ED; a.E = d_emb; a.n_q = nq; a.n_d = n_d;
         a.n_stages = (int)n_stages; a.top_k = top_k; a.active = d_active ? d_active + q0 : nullptr;
-        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.theta_rank = theta_rank; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = collect_cap; a.dbg = dbg;
+        a.theta = d_theta + q0; a.theta_hi = d_theta_hi + q0; a.theta_rank = theta_rank; a.hi_rank = top_k / sample_stride; a.cbuf = d_cbuf; a.ccount = d_cnt; a.cap = collect_cap; a.dbg = dbg;
         a.n_split = 1;
         a.e_tiles = d_es; a.n_stages = (int)s_stages;
         // pass 1 keeps the full split: on data whose scores crowd together a threshold that is off by the hi*hi
@@ -1358,7 +1367,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             int h_flat[2] = {0, 0};
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_flat, d_flat, sizeof h_flat, cudaMemcpyDeviceToHost, st));
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
-            hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.005 * h_flat[1];
+            // (a query without that room is not lost: it fails verification and takes the second chance below,
+            // which is cheap next to the +35 % of a full-split pass)
+            hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.02 * h_flat[1];
             if (mode_env && !strcmp(mode_env, "hionly")) hi_only = true;
             if (getenv("FWAV_UMMA_VERBOSE"))
                 fprintf(stderr, "[fwav] search batch at %lld: %d of %d live queries leave < %.1e between their top_k-th score and theta: %s collect pass\n",
@@ -1440,7 +1451,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
                 hi_only ? kHiOnlySlack : kScoreSlack, d_cand + (q0 + qoff) * top_k,
                 d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
-                top_k > 32 ? d_theta + q0 + qoff : nullptr, key_cap);
+                d_theta + q0 + qoff, key_cap);
             FWAV_LAUNCH_CHECK(ctx);
         }
         if ((rc = mark(ctx, slot, 4, st))) return rc;
@@ -1460,7 +1471,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const size_t sz_q = (size_t)fp * kQPair * ED * sizeof(float), sz_t = (size_t)fp * 2 * kTileBytes,
                          sz_c = (((size_t)n_fail * top_k * sizeof(int32_t)) + 255) & ~(size_t)255,
                          sz_n = (((size_t)n_fail + 4) * sizeof(int) + 255) & ~(size_t)255;
-            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, 2 * sz_q + sz_t + 4 * sz_c + 2 * sz_n, (void **)&blk))) return rc;
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_FB, 2 * sz_q + 2 * sz_t + 4 * sz_c + 2 * sz_n, (void **)&blk))) return rc;
             float *d_fq = reinterpret_cast<float *>(blk);
             uint4 *d_fqt = reinterpret_cast<uint4 *>(blk + sz_q);
             int32_t *d_fc = reinterpret_cast<int32_t *>(blk + sz_q + sz_t);
@@ -1470,28 +1481,28 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             float *d_fq2 = reinterpret_cast<float *>(blk + sz_q + sz_t + 2 * sz_c + 2 * sz_n);
             int32_t *d_fc2 = reinterpret_cast<int32_t *>(blk + 2 * sz_q + sz_t + 2 * sz_c + 2 * sz_n);
             float *d_fs2 = reinterpret_cast<float *>(blk + 2 * sz_q + sz_t + 3 * sz_c + 2 * sz_n);
+            uint4 *d_fqt2 = reinterpret_cast<uint4 *>(blk + 2 * sz_q + sz_t + 4 * sz_c + 2 * sz_n);
             gather_rows_kernel<<<(n_fail * (ED / 4) + 255) / 256, 256, 0, st>>>(d_q + q0 * ED, d_fail, n_fail, d_fq);
             FWAV_LAUNCH_CHECK(ctx);
             pack_f16_tiles_kernel<<<grid_for(ctx, fp * 2 * kDTile * 2), 256, 0, st>>>(d_fq, n_fail, fp * 2, d_fqt, 1);
             FWAV_LAUNCH_CHECK(ctx);
-            if (top_k <= 32) {
-                rc = launch_lists(ctx, d_fqt, d_et, d_fq, d_emb, n_fail, n_d, (int)n_stages, top_k, nullptr, d_fc, d_fs, dbg, st);
-                if (rc) return rc;
-            } else {
-                // No list kernel for top_k > 32, and the FFMA scan costs milliseconds per query on a large table.
-                // Second chance on the tensor cores first: the failed queries alone, same thresholds, full split
-                // (slack 4e-6 instead of 2e-3), the table split between up to eight CTAs per 128 queries, each
-                // with its own candidate buffers: many times the room per query.  What fails again goes to FFMA.
+            {
+                // The exact kernels are expensive for a handful of queries (list kernel: ~3 ms for 40 queries of
+                // config 2; FFMA for top_k > 32: milliseconds per query on a large table).  Second chance on the
+                // tensor cores first: the failed queries alone, full split (slack 4e-6 instead of 2e-3), thresholds
+                // as before or lowered to the K-th score found (boundary cases), the table split between up to
+                // sixteen CTAs per 128 queries, each with its own candidate buffers: many times the room per query.
+                // What fails again goes to the list kernel (top_k <= 32) or the FFMA kernel.
                 const long long fg = (n_fail + kQTile - 1) / kQTile;
                 long long rs = ctx->num_sms / fg;
-                if (rs > 8) rs = 8;
+                if (rs > 16) rs = 16;
                 if (rs > n_stages / 8) rs = n_stages / 8;
                 if (rs < 1) rs = 1;
                 const bool retry = single && (hi_only || rs >= 2) && !(mode_env && !strcmp(mode_env, "noretry"));
                 int n_fail2 = n_fail;
                 const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
                 if (retry) {
-                    const int rcap = rs >= 2 ? collect_cap / 2 : collect_cap;
+                    const int rcap = rs > 8 ? collect_cap / 4 : rs >= 2 ? collect_cap / 2 : collect_cap;
                     int32_t *d_rbuf = nullptr;
                     const size_t nb = (size_t)n_fail * rs * 4 * rcap * sizeof(int32_t), nc = (size_t)n_fail * rs * 4 * sizeof(int);
                     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_rbuf))) return rc;
@@ -1520,7 +1531,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         fprintf(stderr, "[fwav] search batch at %lld: second chance (full split, table split %lld ways): %d of %d fail again (overflow %d, short %d, boundary %d)\n",
                                 q0, rs, n_fail2, n_fail, h_fail2[1], h_fail2[2], h_fail2[3]);
                 }
-                ctx->umma_ffma_queries += n_fail2;
+                ctx->umma_ffma_queries += n_fail2;     // (the list kernel's, for top_k <= 32)
                 if (n_fail2 > 0) {
                     const float *d_in = d_fq;
                     if (d_list2) {
@@ -1528,9 +1539,21 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         FWAV_LAUNCH_CHECK(ctx);
                         d_in = d_fq2;
                     }
-                    if ((rc = fwav_launch_topk_ffma(ctx, d_in, n_fail2, d_emb, n_d, ED, top_k, nullptr, d_list2 ? d_fc2 : d_fc,
-                                                    d_list2 ? d_fs2 : d_fs, st)))
-                        return rc;
+                    if (top_k <= 32) {
+                        const uint4 *d_in_t = d_fqt;
+                        if (d_list2) {
+                            const long long fp2 = (n_fail2 + kQPair - 1) / kQPair;
+                            pack_f16_tiles_kernel<<<grid_for(ctx, fp2 * 2 * kDTile * 2), 256, 0, st>>>(d_fq2, n_fail2, fp2 * 2, d_fqt2, 1);
+                            FWAV_LAUNCH_CHECK(ctx);
+                            d_in_t = d_fqt2;
+                        }
+                        rc = launch_lists(ctx, d_in_t, d_et, d_in, d_emb, n_fail2, n_d, (int)n_stages, top_k, nullptr,
+                                          d_list2 ? d_fc2 : d_fc, d_list2 ? d_fs2 : d_fs, dbg, st);
+                    } else {
+                        rc = fwav_launch_topk_ffma(ctx, d_in, n_fail2, d_emb, n_d, ED, top_k, nullptr, d_list2 ? d_fc2 : d_fc,
+                                                   d_list2 ? d_fs2 : d_fs, st);
+                    }
+                    if (rc) return rc;
                     if (d_list2) {
                         scatter_cand_kernel<<<(n_fail2 * top_k + 255) / 256, 256, 0, st>>>(d_fc2, d_fs2, d_list2, n_fail2, top_k, d_fc, d_fs);
                         FWAV_LAUNCH_CHECK(ctx);

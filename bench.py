@@ -454,9 +454,10 @@ def run_ours(args):
         "config": {"workload": workload_name(w, args.scale), "n_samples": n, "n_ranges": n_r,
                    "n_domains": n_d, "pairs": pairs, "top_k": K, "emb_dim": EMB_DIM,
                    "query_mode": "reference (q_i = E[i])",
-                   "search_impl": ("tcgen05 cta_group::2 fp16 hi/lo split, 256x256 tiles per CTA pair: sampled threshold (3 MMAs/tile), "
-                                   "collect pass (hi*hi term alone when the probe after pass 1 allows it, else 3 MMAs/tile), "
-                                   "exact float32 finalize with per-query verification" if tensor else "FP32 FFMA"),
+                   "search_impl": ("tcgen05 (cta_group::1, M128 N256 K16) fp16 hi/lo split, 128x256 tiles per CTA: threshold pass over a strided "
+                                   "sample (3 MMAs/tile), collect pass (hi*hi term alone when the probe after pass 1 allows it, else "
+                                   "3 MMAs/tile), exact float32 finalize with per-query verification, second tensor-core pass "
+                                   "then exact list/FFMA kernel for queries that fail it" if tensor else "FP32 FFMA"),
                    "parallelism": f"ranges sharded x{world}" + (", tables NCCL-broadcast from rank 0, matches all-gathered" if world > 1 else ""),
                    "l2": "flushed between timed steps (256 MiB device write outside the event pairs)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
