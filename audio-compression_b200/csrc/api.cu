@@ -392,6 +392,28 @@ int fwav_free(fwav_ctx *ctx, void *d_ptr) {
     return FWAV_OK;
 }
 
+int fwav_host_alloc(fwav_ctx *ctx, int64_t bytes, void **h_ptr) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, h_ptr && bytes >= 0, "bad argument");
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes > 0 ? (size_t)bytes : 16, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *h_ptr = nullptr;
+        return fwav_set_error(ctx, FWAV_ERR_NOMEM, "cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return FWAV_OK;
+}
+
+int fwav_host_free(fwav_ctx *ctx, void *h_ptr) {
+    // ctx may be NULL: a buffer can outlive the context it was allocated through (portable allocation)
+    (void)ctx;
+    if (h_ptr && cudaFreeHost(h_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return FWAV_ERR_CUDA;
+    }
+    return FWAV_OK;
+}
+
 int fwav_memcpy_h2d(fwav_ctx *ctx, void *d_dst, const void *h_src, int64_t bytes, void *stream) {
     FWAV_ENTER(ctx);
     cudaStream_t st = fwav_stream(ctx, stream);

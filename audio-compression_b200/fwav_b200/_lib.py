@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -63,6 +64,8 @@ SIGNATURES = [
                                    C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     ("fwav_malloc", C.c_int, [c_ctx, i64, C.POINTER(c_ptr)]),
     ("fwav_free", C.c_int, [c_ctx, c_ptr]),
+    ("fwav_host_alloc", C.c_int, [c_ctx, i64, C.POINTER(c_ptr)]),
+    ("fwav_host_free", C.c_int, [c_ctx, c_ptr]),
     ("fwav_memcpy_h2d", C.c_int, [c_ctx, c_ptr, c_ptr, i64, c_ptr]),
     ("fwav_memcpy_d2h", C.c_int, [c_ctx, c_ptr, c_ptr, i64, c_ptr]),
 ]
@@ -209,6 +212,26 @@ class Context:
         return DeviceBuffer(self, nbytes)
 
     # ---- host-buffer entry points (what fractal.compress_audio / decompress_audio call) ----
+    def pinned_empty(self, shape, dtype):
+        """numpy array in page-locked host memory (freed when the array and its views are gone) when
+        FWAV_PINNED=1, else a plain pageable one.  Opt-in: page-locking fresh memory on every call costs more
+        than the staged copies it avoids (config 2 through compress_audio_arrays on B200: 290-510 ms per call
+        with per-call pinned buffers against 148 ms with pageable ones; fwav_compress_host on buffers that are
+        pinned ONCE and reused takes 79.5 ms).  Callers that keep their buffers should allocate them once with
+        this and pass them as `out=`."""
+        dtype = np.dtype(dtype)
+        shape = (shape,) if np.isscalar(shape) else tuple(shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes == 0 or os.environ.get("FWAV_PINNED", "0") != "1":
+            return np.empty(shape, dtype)
+        p = c_ptr()
+        if self.lib.fwav_host_alloc(self.h, nbytes, C.byref(p)) != 0 or not p.value:
+            return np.empty(shape, dtype)
+        buf = (C.c_ubyte * nbytes).from_address(p.value)
+        lib, addr = self.lib, p.value
+        weakref.finalize(buf, lib.fwav_host_free, None, addr)   # numpy keeps `buf` alive through .base
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
     def compress_host(self, signal, ranges, tile_size, emb_dim, top_k, energy_thresh, fast_mode=True,
                       query_mode=0, want_domains=True, out=None):
         signal = _as(signal, np.float32)
@@ -217,10 +240,11 @@ class Context:
         rs, ds = geometry(tile_size)
         n_d = count_domains(len(signal), tile_size, ds)
         if out is None:
+            pe = self.pinned_empty
             out = dict(
-                domains=np.empty((n_d, rs), np.float32) if want_domains else None,
-                idx=np.empty(n_r, np.int32), s=np.empty(n_r, np.float32), o=np.empty(n_r, np.float32),
-                sym=np.empty(n_r, np.uint8), err=np.empty(n_r, np.float32))
+                domains=pe((n_d, rs), np.float32) if want_domains else None,
+                idx=pe(n_r, np.int32), s=pe(n_r, np.float32), o=pe(n_r, np.float32),
+                sym=pe(n_r, np.uint8), err=pe(n_r, np.float32))
         self._check(self.lib.fwav_compress_host(
             self.h, _hp(signal), len(signal), _hp(ranges), n_r, int(tile_size), int(emb_dim), int(top_k),
             float(energy_thresh), int(bool(fast_mode)), int(query_mode), _hp(out["domains"]),

@@ -174,6 +174,12 @@ int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains,
  * drive the device-pointer entry points. */
 int fwav_malloc(fwav_ctx *ctx, int64_t bytes, void **d_ptr);
 int fwav_free(fwav_ctx *ctx, void *d_ptr);
+/* Page-locked host memory for the buffers handed to fwav_compress_host / fwav_decode_host: with pageable
+ * buffers the result copies are staged by the driver and cannot overlap the search (config 2: the 127 MB domain
+ * table).  Portable across contexts; free with fwav_host_free (its ctx argument may be NULL: a buffer may
+ * outlive the context it was allocated through). */
+int fwav_host_alloc(fwav_ctx *ctx, int64_t bytes, void **h_ptr);
+int fwav_host_free(fwav_ctx *ctx, void *h_ptr);
 int fwav_memcpy_h2d(fwav_ctx *ctx, void *d_dst, const void *h_src, int64_t bytes, void *stream);
 int fwav_memcpy_d2h(fwav_ctx *ctx, void *h_dst, const void *d_src, int64_t bytes, void *stream);
 
