@@ -10,19 +10,20 @@
 // (scripts/umma_microbench.cu on B200: 118 cycles for M=128 N=128 K=16 whatever the
 // operand layout, 173 for the CTA-pair M=256 N=256 one that does four times the work).
 //
-// One kernel skeleton (scan_kernel<MODE>), shared by three epilogues:
-//   * a CLUSTER OF TWO CTAs (one TPC) owns 256 queries, 128 per CTA, and issues
-//     tcgen05.mma.cta_group::2 with M=256, N=256: each CTA keeps its own 128 query
-//     rows (A) and HALF of every 256-domain stage (B) in shared memory, so every
-//     domain tile is read from L2 once per 256 queries;
+// One kernel skeleton (scan_kernel<MODE, HI, CG>), shared by three epilogues:
+//   * CG = 2 (the exact list kernel): a CLUSTER OF TWO CTAs (one TPC) owns 256 queries, 128 per CTA, and
+//     issues tcgen05.mma.cta_group::2 with M=256, N=256: each CTA keeps its own 128 query rows (A) and HALF
+//     of every 256-domain stage (B) in shared memory; commits are multicast to the mbarriers of BOTH CTAs and
+//     the peer relays "my half of the stage has landed" with a remote mbarrier arrive.
+//     CG = 1 (the streaming passes): a CTA on its own, M=128, N=256, both tiles of a stage in its shared
+//     memory: the same tensor rate per SM and no cross-CTA signalling in the hand-over chain;
 //   * operands are pre-split into fp16 hi/lo parts (x = hi + lo, 22 significant
 //     bits) and pre-tiled by a pack kernel into the K-major SWIZZLE_32B UMMA layout,
 //     so one plain bulk copy (cp.async.bulk, the TMA engine, no tensor map) lands a
 //     128-domain tile in shared memory ready for the tensor core;
-//   * per stage three K=16 instructions (hi*lo, lo*hi, hi*hi) go into one of two
-//     256-column TMEM accumulator buffers; two issuing threads in the leader CTA,
-//     one per buffer; commits are multicast to the mbarriers of BOTH CTAs; the peer
-//     CTA relays "my half of the stage has landed" with a remote mbarrier arrive;
+//   * per stage three K=16 instructions (hi*lo, lo*hi, hi*hi) -- or the hi*hi one alone (HI) where a filter
+//     with a 2e-3 error bound is enough -- go into one of two 256-column TMEM accumulator buffers; two
+//     issuing threads, one per buffer;
 //   * epilogue warps read the accumulators with tcgen05.ld 32x32b.x32 — one query
 //     row per thread — hand the buffer back as soon as their share is in registers,
 //     reduce each 32-column chunk to its maximum with 3-input max instructions and
@@ -32,7 +33,8 @@
 // MODE_THETA + MODE_COLLECT + finalize_kernel are the fast path: a per-query
 // threshold from a strided sample of the table, one scan that only appends the
 // indices of the domains that reach it, then an exact re-score with a proof that
-// nothing was missed.  Either way every returned candidate carries the canonical
+// nothing was missed; queries that fail the proof get a second, full-split pass with
+// their own buffers and only then an exact kernel.  Either way every returned candidate carries the canonical
 // float32 score (ascending-k FMA chain) and the rows are ordered by it, ties by
 // index: the result equals the FFMA kernel's bit for bit.
 //
@@ -81,7 +83,7 @@ constexpr uint32_t kOffBars = kOffA + kTileBytes;
 constexpr uint32_t kBarBytes = 16 * kStages + 72;      // full[], empty[], tfull[2], tempty[2], a, done[2], tmem slot
 constexpr uint32_t kOffMode = kOffBars + 256;
 static_assert(kBarBytes <= 256, "barrier block");
-constexpr int kTheta = 16;             // threshold = kTheta-th largest score against the sample table
+constexpr int kTheta = 16;             // ranks of the merged sample list the probe may ask for; default threshold rank is kTheta / 2
 constexpr int kThetaPart = 6;          // kept per column group (four groups per row)
 constexpr int kThetaWarm = 24;         // first stages of pass 1 that only look at chunk maxima
 // MODE_LISTS: [row][column half][kCap] keys, then one owner's 128 scores per warp
@@ -110,8 +112,8 @@ struct ScanArgs {
     float *scores;             // MODE_LISTS out (optional)
     float *theta;              // MODE_THETA out, MODE_COLLECT in
     int hi_rank;               // MODE_THETA: which sampled score estimates the top_k-th best of the table (top_k / stride)
-    int theta_rank;            // MODE_THETA: which of the merged best sampled scores becomes theta (16 .. 24)
-    float *theta_hi;           // MODE_THETA out: the (top_k / 16)-th best sampled score (about the top_k-th of the table)
+    int theta_rank;            // MODE_THETA: which of the merged best sampled scores becomes theta (1 .. 24)
+    float *theta_hi;           // MODE_THETA out: the hi_rank-th best sampled score (about the top_k-th of the table)
     int32_t *cbuf;             // MODE_COLLECT out: [query][split][column group][cap] domain indices
     int *ccount;               // MODE_COLLECT out: [query][split][column group] how many passed (may exceed cap)
     int cap;
