@@ -935,6 +935,167 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 // that fail (too few candidates, buffer overflow, boundary within the slack) go
 // on the list for the exact MODE_LISTS kernel.
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// EXPERIMENTAL (FWAV_UMMA_QUAD=1; written at the end of round 1, NOT yet run on a GPU -- the default path never
+// reaches it): the collect pass with FOUR 128-column accumulator buffers, two per epilogue set.
+// DESIGN.md section 7 has the arithmetic: with two 256-column buffers a set of epilogue warps idles while its only
+// buffer goes through the MMA hand-over; here a stage is one 128-domain tile (M128 N128 K16 MMAs), set s takes
+// the tiles t = s (mod 2) and alternates between buffers s and s + 2, a warp takes 64 columns of an own tile
+// (one pair of loads) and hands the buffer back right after the loads.  Same inputs, outputs and candidate-buffer
+// layout as scan_kernel<MODE_COLLECT, HI, 1> (group = set + 2 * column half), so finalize_kernel does not care.
+// ---------------------------------------------------------------------------
+constexpr int kQuadRing = 16;                                  // 128-domain tiles in flight (8 KB each: hi | lo)
+constexpr uint32_t kQuadOffBars = kTileBytes;                  // after the query tile
+constexpr uint32_t kQuadOffRing = kTileBytes + 1024;           // 1024-aligned
+constexpr uint32_t kQuadSmem = kQuadOffRing + kQuadRing * kTileBytes;
+constexpr uint32_t kQuadIdesc = (1u << 4) | ((uint32_t)(kDTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);   // D=F32, A=B=F16, N=128, M=128
+
+__device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kQuadIdesc), "r"(accumulate)
+        : "memory");
+}
+
+template <bool HI>
+__global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kernel(const ScanArgs a) {
+    constexpr int kEpi = 16, kThreads = n_threads(MODE_COLLECT);
+    constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_q = a.n_q;
+    const int dbg = a.dbg;
+    const uint8_t *__restrict__ active = a.active;
+    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
+    const long long q_base = (long long)group_id * kQTile;
+    const uint32_t bars = smem_u32(smem + kQuadOffBars);
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQuadRing, bar_tfull = bars + 16 * kQuadRing,
+                   bar_tempty = bar_tfull + 32, bar_a = bar_tempty + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQuadOffBars + 16 * kQuadRing + 80);
+
+    {   // energy-pruned stretch: nothing to scan
+        int any = 0;
+        for (int i = threadIdx.x; i < kQTile; i += kThreads) {
+            const long long q = q_base + i;
+            if (q < n_q && (!active || active[q])) any = 1;
+        }
+        if (!__syncthreads_or(any)) {
+            for (int i = threadIdx.x; i < kQTile; i += kThreads) {
+                const long long q = q_base + i;
+                if (q < n_q)
+                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kQuadRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kEpi / 2); }
+        mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpi) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // this CTA's share of the table, in 128-domain tiles; the scan starts at the CTA's own rows and wraps around
+    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
+    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;
+    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
+
+    if (warp == kEpi) {
+        // ===== producer: one bulk copy per tile ([hi | lo] is contiguous in the packed table) =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, kOpBytes);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kOpBytes, bar_a);
+            int tt = t_first;
+            for (int t = 0; t < n_visit; ++t) {
+                const int s = t & (kQuadRing - 1);
+                mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / kQuadRing) & 1) ^ 1));
+                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
+                bulk_g2s(smem_u32(smem + kQuadOffRing + s * kTileBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kOpBytes,
+                         bar_full + 8 * s);
+                if (++tt == t_hi) tt = t_lo;
+            }
+        }
+    } else if (warp > kEpi) {
+        // ===== two MMA issuers: thread i owns the tiles t = i (mod 2), i.e. buffers i and i + 2 =====
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            const uint32_t a_hi = smem_u32(smem + kOffA);
+            const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_hi + kPartBytes);
+            for (int t = warp - (kEpi + 1); t < n_visit; t += 2) {
+                const int s = t & (kQuadRing - 1), buf = t & 3;
+                const uint32_t b_hi = smem_u32(smem + kQuadOffRing + s * kTileBytes);
+                const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_hi + kPartBytes);
+                const uint32_t d = tmem_base + (uint32_t)(buf * kDTile);
+                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQuadRing) & 1));
+                mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((t >> 2) & 1) ^ 1));
+                tc_fence_after();
+                if (HI) {
+                    umma_f16_m128n128(d, da_hi, db_hi, 0);
+                } else {
+                    umma_f16_m128n128(d, da_hi, db_lo, 0);
+                    umma_f16_m128n128(d, da_lo, db_hi, 1);
+                    umma_f16_m128n128(d, da_hi, db_hi, 1);
+                }
+                umma_commit<1>(bar_tfull + 8 * buf);
+                umma_commit<1>(bar_empty + 8 * s);
+            }
+        }
+    } else {
+        // ===== epilogue: one query row per thread; warp = (lane quadrant, set, column half of the tile) =====
+        const int quad = warp & 3, grp = warp >> 2, set = grp & 1, colhalf = grp >> 1;
+        const long long q = q_base + quad * 32 + lane;
+        const float tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
+        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + grp) * (long long)a.cap;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(colhalf * 64);
+        int cnt = 0;
+        int tt = t_first + set;
+        if (tt >= t_hi) tt -= n_visit;
+        for (int t = set; t < n_visit; t += 2) {
+            const int buf = t & 3;
+            mbar_wait_hot(bar_tfull + 8 * buf, (uint32_t)((t >> 2) & 1));
+            tc_fence_after();
+            uint32_t x0[32], x1[32];
+            tmem_ld32(t_lane + (uint32_t)(buf * kDTile), x0);
+            tmem_ld32(t_lane + (uint32_t)(buf * kDTile) + 32, x1);
+            tmem_wait_ld2(x0, x1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
+            const float ma = chunk_max(x0);
+            const int col0 = tt * kDTile + colhalf * 64;
+            tt += 2;
+            if (tt >= t_hi) tt -= n_visit;
+            const float mb = chunk_max(x1);
+            if (ma >= tau)
+                for_each_ge(x0, tau, [&](int j) {
+                    if (cnt < a.cap) cbuf[cnt] = col0 + j;
+                    ++cnt;
+                });
+            if (mb >= tau)
+                for_each_ge(x1, tau, [&](int j) {
+                    if (cnt < a.cap) cbuf[cnt] = col0 + 32 + j;
+                    ++cnt;
+                });
+        }
+        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + grp] = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpi) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core score - canonical float32 score| (measured max 3.9e-7)
 // hi*hi term alone: inputs rounded to fp16 (relative 2^-11 each), sum |q_k e_k| <= |q||e| <= 2 (two unit heads):
 // 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
@@ -1216,6 +1377,19 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
     return FWAV_OK;
 }
 
+// the experimental four-buffer collect pass (FWAV_UMMA_QUAD=1): one CTA per 128 queries and table share
+template <bool HI>
+int launch_quad(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
+        attr_set = true;
+    }
+    collect_quad_kernel<HI><<<(unsigned)(groups * split), n_threads(MODE_COLLECT), kQuadSmem, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
 // record phase boundary k of timed batch `slot` (events are created on first use)
 int mark(fwav_ctx *ctx, int slot, int k, cudaStream_t st) {
     if (slot >= fwav_ctx::kSearchSlots) return FWAV_OK;
@@ -1315,6 +1489,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     FWAV_LAUNCH_CHECK(ctx);
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
+    const char *quad_env = getenv("FWAV_UMMA_QUAD");          // experimental four-buffer collect pass (see collect_quad_kernel)
+    const bool quad = single && quad_env && atoi(quad_env) == 1;
     const long long batch = n_q < kBatchQueries ? n_q : kBatchQueries;
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
@@ -1417,7 +1593,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
-            if (hi_only)
+            if (quad)
+                rc = hi_only ? launch_quad<true>(ctx, ax, g, sp, st) : launch_quad<false>(ctx, ax, g, sp, st);
+            else if (hi_only)
                 rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);
             else
                 rc = single ? launch_scan<MODE_COLLECT, false, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, false, 2>(ctx, ax, g, sp, st);
@@ -1515,7 +1693,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     ar.q_tiles = d_fqt; ar.Q = d_fq; ar.n_q = n_fail; ar.active = nullptr; ar.theta = d_ftheta;
                     ar.n_split = (int)rs; ar.cbuf = d_rbuf; ar.cap = rcap;
                     ar.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_rbuf) + nb);
-                    if ((rc = launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st))) return rc;
+                    if ((rc = quad ? launch_quad<false>(ctx, ar, fg, rs, st) : launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st)))
+                        return rc;
                     const int parts = 4 * (int)rs;
                     const size_t fin_smem = (size_t)kFinWarps * parts * rcap * sizeof(unsigned long long);
                     if (fin_smem > 48 * 1024)

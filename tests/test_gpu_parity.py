@@ -10,6 +10,8 @@ Gates (BASELINE.json north_star):
     relative; s, o within 1e-5 relative (bit-identical given equal candidates);
   * decoded audio: bit-identical to the oracle (the gate asks for 1e-4 max-abs).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -501,6 +503,36 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         sc = e.astype(np.float64) @ q[i].astype(np.float64)
         kth = np.sort(sc)[-top_k]
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
+
+
+@pytest.mark.skipif(os.environ.get("FWAV_TEST_EXPERIMENTAL") != "1",
+                    reason="collect_quad_kernel (FWAV_UMMA_QUAD=1) was written after round 1's GPU budget was spent: "
+                           "not yet run on a device; set FWAV_TEST_EXPERIMENTAL=1 to try it")
+@pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None)])
+def test_experimental_four_buffer_collect(ctx, monkeypatch, n_q, top_k, mode):
+    """The four-buffer collect pass must return what the FFMA kernel returns (same table as the odd-shapes test)."""
+    monkeypatch.setenv("FWAV_UMMA_QUAD", "1")
+    if mode:
+        monkeypatch.setenv("FWAV_UMMA_MODE", mode)
+    ED = 16
+    n_d = (1 << 17) + 77
+    rng = np.random.default_rng(300 + n_q)
+    e = rng.standard_normal((n_d, ED)).astype(np.float32)
+    for h in (slice(0, 8), slice(8, 16)):
+        e[:, h] /= np.linalg.norm(e[:, h], axis=1, keepdims=True)
+    q = np.ascontiguousarray(e[rng.choice(n_d, n_q, replace=False)] + (rng.standard_normal((n_q, ED)) * 0.05).astype(np.float32))
+    d_e, d_q = ctx.upload(e), ctx.upload(q)
+    out = {}
+    for impl in ("ffma", "umma"):
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * top_k * 4), ctx.alloc(n_q * top_k * 4)
+        try:
+            ctx.topk(d_q.ptr, n_q, d_e.ptr, n_d, ED, top_k, None, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32))
+    assert np.array_equal(out["umma"][0], out["ffma"][0])
+    assert np.array_equal(bits(out["umma"][1]), bits(out["ffma"][1]))
 
 
 def test_config2_full_size_sample(ctx):
