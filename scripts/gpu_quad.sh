@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 opener for the experimental four-buffer collect pass: parity first, then the
+# config-2 search with and without it, then the config-4 shape at 1/10 length (full split).
+mkdir -p gpurun_out; rm -f gpurun_out/quad.txt
+FWAV_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "experimental_four_buffer" 2>&1 | tail -5 > gpurun_out/quad_tests.txt
+cat gpurun_out/quad_tests.txt
+grep -q "passed" gpurun_out/quad_tests.txt || exit 1
+for quad in 0 1; do
+  echo "== FWAV_UMMA_QUAD=$quad (config 2)" >> gpurun_out/quad.txt
+  FWAV_UMMA_QUAD=$quad FWAV_UMMA_VERBOSE=1 timeout 200 python scripts/time_topk.py 1.0 umma 3 > gpurun_out/quad_run.out 2> gpurun_out/quad_run.err
+  grep "fwav\]" gpurun_out/quad_run.err | tail -3 | cut -c1-200 >> gpurun_out/quad.txt
+  cut -c1-260 gpurun_out/quad_run.out >> gpurun_out/quad.txt
+  echo "== FWAV_UMMA_QUAD=$quad FWAV_UMMA_MODE=precise (config 2, full split)" >> gpurun_out/quad.txt
+  FWAV_UMMA_QUAD=$quad FWAV_UMMA_MODE=precise timeout 200 python scripts/time_topk.py 1.0 umma 2 2>/dev/null | cut -c1-260 >> gpurun_out/quad.txt
+done
+cat gpurun_out/quad.txt
