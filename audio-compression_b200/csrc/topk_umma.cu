@@ -310,6 +310,74 @@ pack_f16_tiles_kernel(const float *__restrict__ src, long long n_rows, long long
 }
 
 // ---------------------------------------------------------------------------
+// EXPERIMENTAL (FWAV_UMMA_COMPACT=1; written at the end of round 1, NOT yet run on a GPU): compact split.
+// With range_size 4 (the reference's default tile_size 1024, BASELINE config 4) only 7 of the 16 embedding
+// dimensions are ever non-zero (3 tonal + 4 transient, fractal.py:154-208).  Eight live dimensions leave room for
+// the hi AND the lo part in one K = 16 operand, so the full split needs two MMAs per stage instead of three:
+//     queries   part 0 = [q_hi | q_lo]   part 1 = [q_hi | 0]
+//     domains   part 0 = [e_hi | e_hi]   part 1 = [e_lo | 0]
+//     part 0 . part 0 = hi*hi + lo*hi        part 1 . part 1 = hi*lo
+// The parts sit where the hi / lo parts of pack_f16_tiles_kernel sit, so the hi*hi-only variant (part 0 alone)
+// works unchanged and is a little more accurate (q . e_hi instead of q_hi . e_hi).
+// ---------------------------------------------------------------------------
+struct LivePerm { int n; int dim[8]; };
+
+__global__ void live_dims_kernel(const float *__restrict__ x, long long n_rows, unsigned *__restrict__ mask) {
+    unsigned m = 0;
+    const long long total = n_rows * (ED / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        const int k = (int)(i % (ED / 4)) * 4;
+        m |= (v.x != 0.f ? 1u : 0u) << k | (v.y != 0.f ? 1u : 0u) << (k + 1) | (v.z != 0.f ? 1u : 0u) << (k + 2) |
+             (v.w != 0.f ? 1u : 0u) << (k + 3);
+    }
+    m = __reduce_or_sync(kFull, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(mask, m);
+}
+
+// role 0: query tiles, role 1: domain tiles (see above); same tiling, swizzle and sample dealing as pack_f16_tiles_kernel
+__global__ void __launch_bounds__(256)
+pack_compact_tiles_kernel(const float *__restrict__ src, long long n_rows, long long n_tiles, uint4 *__restrict__ dst,
+                          int row_stride, LivePerm perm, int role) {
+    const long long total = n_tiles * (kDTile * 2);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const long long tile = g / (kDTile * 2);
+        const int w = (int)(g - tile * (kDTile * 2));
+        const int c = w / kDTile, r = w % kDTile;       // c: which 16-byte chunk of the 32-byte operand row
+        long long row = tile * kDTile + r;
+        if (row_stride > 1) {
+            const long long in_stage = row & (kDStage - 1);
+            row = ((row & ~(long long)(kDStage - 1)) + (in_stage & 63) * 4 + (in_stage >> 6)) * row_stride;
+        }
+        float xs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row < n_rows) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < perm.n) xs[k] = __ldg(src + row * ED + perm.dim[k]);
+        }
+        __half2 hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half h0 = __float2half_rn(xs[2 * i]), h1 = __float2half_rn(xs[2 * i + 1]);
+            hi[i] = __halves2half2(h0, h1);
+            lo[i] = __halves2half2(__float2half_rn(xs[2 * i] - __half2float(h0)),
+                                   __float2half_rn(xs[2 * i + 1] - __half2float(h1)));
+        }
+        const uint4 vhi = *reinterpret_cast<const uint4 *>(hi), vlo = *reinterpret_cast<const uint4 *>(lo);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *t = dst + tile * (2 * kDTile * 2);
+        const int slot = (r >> 3) * 16 + (r & 7) * 2 + (c ^ ((r >> 2) & 1));
+        if (role == 0) {
+            t[slot] = c == 0 ? vhi : vlo;                       // part 0 = [hi | lo]
+            t[kDTile * 2 + slot] = c == 0 ? vhi : zero;         // part 1 = [hi | 0]
+        } else {
+            t[slot] = vhi;                                      // part 0 = [hi | hi]
+            t[kDTile * 2 + slot] = c == 0 ? vlo : zero;         // part 1 = [lo | 0]
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Candidate bookkeeping.  A candidate is one 64-bit key
 //     [ order-preserving bits of the score | 0xFFFFFFFF - domain index ]
 // so "ranks before" (score descending, index ascending) is a plain unsigned
@@ -480,8 +548,9 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
 #define FWAV_ALT_SETS 1
 #endif
 
-template <int MODE, bool HI, int CG>
+template <int MODE, bool HI, int CG, bool COMPACT = false>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
+    static_assert(!(HI && COMPACT), "the hi*hi-only variant reads part 0 alone: no separate compact form");
     // hi*hi-only collect pass: the sixteen epilogue warps form two sets, one per TMEM buffer.  A set takes every
     // other stage (128 columns per warp), so while one set waits for its tcgen05.ld the other one is reducing;
     // with all warps on every stage they move in lockstep and the load time adds to the ALU time (collect pass of
@@ -647,6 +716,9 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
                 if (HI) {
                     umma_f16<CG>(d, da_hi, db_hi, 0);
+                } else if (COMPACT) {
+                    umma_f16<CG>(d, da_lo, db_lo, 0);      // part 1 . part 1 = hi*lo
+                    umma_f16<CG>(d, da_hi, db_hi, 1);      // part 0 . part 0 = hi*hi + lo*hi
                 } else {
                     umma_f16<CG>(d, da_hi, db_lo, 0);
                     umma_f16<CG>(d, da_lo, db_hi, 1);
@@ -959,7 +1031,7 @@ __device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_de
         : "memory");
 }
 
-template <bool HI>
+template <bool HI, bool COMPACT = false>
 __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kernel(const ScanArgs a) {
     constexpr int kEpi = 16, kThreads = n_threads(MODE_COLLECT);
     constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;
@@ -1040,6 +1112,9 @@ __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kerne
                 tc_fence_after();
                 if (HI) {
                     umma_f16_m128n128(d, da_hi, db_hi, 0);
+                } else if (COMPACT) {
+                    umma_f16_m128n128(d, da_lo, db_lo, 0);
+                    umma_f16_m128n128(d, da_hi, db_hi, 1);
                 } else {
                     umma_f16_m128n128(d, da_hi, db_lo, 0);
                     umma_f16_m128n128(d, da_lo, db_hi, 1);
@@ -1364,28 +1439,28 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
 }
 
 // one launch of the scan skeleton: `groups` tensor-core groups of 128 * CG queries, each scanned by `split` of them
-template <int MODE, bool HI, int CG>
+template <int MODE, bool HI, int CG, bool COMPACT = false>
 int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
     constexpr int smem = (int)smem_bytes(MODE, CG);
     static bool attr_set = false;          // per process; the attribute is per function, not per context
     if (!attr_set) {
-        FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    scan_kernel<MODE, HI, CG><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
+    scan_kernel<MODE, HI, CG, COMPACT><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
 
 // the experimental four-buffer collect pass (FWAV_UMMA_QUAD=1): one CTA per 128 queries and table share
-template <bool HI>
+template <bool HI, bool COMPACT = false>
 int launch_quad(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
+        FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
         attr_set = true;
     }
-    collect_quad_kernel<HI><<<(unsigned)(groups * split), n_threads(MODE_COLLECT), kQuadSmem, st>>>(a);
+    collect_quad_kernel<HI, COMPACT><<<(unsigned)(groups * split), n_threads(MODE_COLLECT), kQuadSmem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1401,7 +1476,7 @@ int mark(fwav_ctx *ctx, int slot, int k, cudaStream_t st) {
 // exact list kernel over packed tiles (small tables, forced mode, fallback of the fast path)
 int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const float *d_q, const float *d_emb, long long n_q,
                  long long n_d, int n_stages, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores, int dbg,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool compact = false) {
     ScanArgs a = {};
     a.q_tiles = d_qt; a.e_tiles = d_et; a.Q = d_q; a.E = d_emb; a.n_q = n_q; a.n_d = n_d;
     a.n_stages = n_stages; a.top_k = top_k; a.active = d_active; a.cand = d_cand; a.scores = d_scores;
@@ -1421,7 +1496,11 @@ int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const floa
         int rc;
         if ((rc = fwav_ws_reserve(ctx, WS_UMMA_PARTS, (size_t)n_q * split * 2 * kCap * 8, (void **)&a.parts))) return rc;
     }
-    { int rc = launch_scan<MODE_LISTS, false, 2>(ctx, a, q_pairs, split, st); if (rc) return rc; }
+    {
+        int rc = compact ? launch_scan<MODE_LISTS, false, 2, true>(ctx, a, q_pairs, split, st)
+                         : launch_scan<MODE_LISTS, false, 2>(ctx, a, q_pairs, split, st);
+        if (rc) return rc;
+    }
     if (split > 1) {
         merge_parts_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_q, d_emb, n_q, (int)split, top_k, d_active, a.parts,
                                                                     d_cand, d_scores);
@@ -1452,10 +1531,44 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_Q, (size_t)q_tiles * kTileBytes, (void **)&d_qt))) return rc;
     ctx->search_slots_used = 0;
     if ((rc = mark(ctx, 0, 0, st))) return rc;
-    pack_f16_tiles_kernel<<<grid_for(ctx, e_tiles * kDTile * 2), 256, 0, st>>>(d_emb, n_d, e_tiles, d_et, 1);
-    FWAV_LAUNCH_CHECK(ctx);
-    pack_f16_tiles_kernel<<<grid_for(ctx, q_tiles * kDTile * 2), 256, 0, st>>>(d_q, n_q, q_tiles, d_qt, 1);
-    FWAV_LAUNCH_CHECK(ctx);
+    // EXPERIMENTAL compact split (FWAV_UMMA_COMPACT=1, see pack_compact_tiles_kernel): which dimensions are live?
+    LivePerm perm = {};
+    bool compact = false;
+    {
+        const char *c_env = getenv("FWAV_UMMA_COMPACT"), *cg2_env = getenv("FWAV_UMMA_CG");
+        if (c_env && atoi(c_env) == 1 && !(cg2_env && atoi(cg2_env) == 2) && n_d >= (1 << 16)) {
+            unsigned *d_mask = nullptr;
+            if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, 2 * sizeof(unsigned), (void **)&d_mask))) return rc;
+            FWAV_CUDA(ctx, cudaMemsetAsync(d_mask, 0, 2 * sizeof(unsigned), st));
+            live_dims_kernel<<<grid_for(ctx, n_d * (ED / 4)), 256, 0, st>>>(d_emb, n_d, d_mask);
+            FWAV_LAUNCH_CHECK(ctx);
+            live_dims_kernel<<<grid_for(ctx, n_q * (ED / 4)), 256, 0, st>>>(d_q, n_q, d_mask + 1);
+            FWAV_LAUNCH_CHECK(ctx);
+            unsigned h_mask[2] = {0, 0};
+            FWAV_CUDA(ctx, cudaMemcpyAsync(h_mask, d_mask, sizeof h_mask, cudaMemcpyDeviceToHost, st));
+            FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+            const unsigned live = h_mask[0] & h_mask[1];    // a dimension dead on either side adds exactly 0 to every score
+            if (__builtin_popcount(live) <= 8) {
+                compact = true;
+                for (int k = 0; k < ED; ++k)
+                    if (live >> k & 1) perm.dim[perm.n++] = k;
+            }
+            if (getenv("FWAV_UMMA_VERBOSE"))
+                fprintf(stderr, "[fwav] live embedding dimensions: table %04x, queries %04x: %s split\n", h_mask[0], h_mask[1],
+                        compact ? "compact (2 MMAs per stage)" : "plain");
+        }
+    }
+    // row-major float32 -> packed fp16 tiles (role 0: queries, 1: domains; stride > 1: the sample table of pass 1)
+    auto pack = [&](const float *src, long long rows, long long tiles, uint4 *dst, int stride, int role) -> int {
+        if (compact)
+            pack_compact_tiles_kernel<<<grid_for(ctx, tiles * kDTile * 2), 256, 0, st>>>(src, rows, tiles, dst, stride, perm, role);
+        else
+            pack_f16_tiles_kernel<<<grid_for(ctx, tiles * kDTile * 2), 256, 0, st>>>(src, rows, tiles, dst, stride);
+        FWAV_LAUNCH_CHECK(ctx);
+        return FWAV_OK;
+    };
+    if ((rc = pack(d_emb, n_d, e_tiles, d_et, 1, 1))) return rc;
+    if ((rc = pack(d_q, n_q, q_tiles, d_qt, 1, 0))) return rc;
     const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
@@ -1464,7 +1577,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if (!fast) {
         for (int k = 1; k <= 4; ++k)
             if ((rc = mark(ctx, 0, k, st))) return rc;
-        if ((rc = launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st)))
+        if ((rc = launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st, compact)))
             return rc;
         if ((rc = mark(ctx, 0, 5, st))) return rc;
         ctx->search_slots_used = 1;
@@ -1485,8 +1598,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const long long s_stages = (n_samp + kDStage - 1) / kDStage;
     uint4 *d_es = nullptr;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_MISC, (size_t)s_stages * 2 * kTileBytes, (void **)&d_es))) return rc;
-    pack_f16_tiles_kernel<<<grid_for(ctx, s_stages * 2 * kDTile * 2), 256, 0, st>>>(d_emb, n_d, s_stages * 2, d_es, sample_stride);
-    FWAV_LAUNCH_CHECK(ctx);
+    if ((rc = pack(d_emb, n_d, s_stages * 2, d_es, sample_stride, 1))) return rc;
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
     const char *quad_env = getenv("FWAV_UMMA_QUAD");          // experimental four-buffer collect pass (see collect_quad_kernel)
@@ -1534,7 +1646,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         // error (1e-3) lands hundreds of ranks away from where it should
         // streaming modes: CTAs on their own by default (FWAV_UMMA_CG=2: CTA pairs)
         const long long groups = single ? (nq + kQTile - 1) / kQTile : pairs;
-        if ((rc = single ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st) : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
+        if ((rc = compact ? launch_scan<MODE_THETA, false, 1, true>(ctx, a, groups, 1, st)
+                  : single ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st)
+                           : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
             return rc;
         // may pass 2 filter with the hi*hi term too?  Only if (nearly) every query has room for its error bound
         bool hi_only = false;
@@ -1594,7 +1708,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
             if (quad)
-                rc = hi_only ? launch_quad<true>(ctx, ax, g, sp, st) : launch_quad<false>(ctx, ax, g, sp, st);
+                rc = hi_only ? launch_quad<true>(ctx, ax, g, sp, st)
+                   : compact ? launch_quad<false, true>(ctx, ax, g, sp, st) : launch_quad<false>(ctx, ax, g, sp, st);
+            else if (compact && !hi_only)
+                rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
             else if (hi_only)
                 rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);
             else
@@ -1664,8 +1781,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             uint4 *d_fqt2 = reinterpret_cast<uint4 *>(blk + 2 * sz_q + sz_t + 4 * sz_c + 2 * sz_n);
             gather_rows_kernel<<<(n_fail * (ED / 4) + 255) / 256, 256, 0, st>>>(d_q + q0 * ED, d_fail, n_fail, d_fq);
             FWAV_LAUNCH_CHECK(ctx);
-            pack_f16_tiles_kernel<<<grid_for(ctx, fp * 2 * kDTile * 2), 256, 0, st>>>(d_fq, n_fail, fp * 2, d_fqt, 1);
-            FWAV_LAUNCH_CHECK(ctx);
+            if ((rc = pack(d_fq, n_fail, fp * 2, d_fqt, 1, 0))) return rc;
             {
                 // The exact kernels are expensive for a handful of queries (list kernel: ~3 ms for 40 queries of
                 // config 2; FFMA for top_k > 32: milliseconds per query on a large table).  Second chance on the
@@ -1693,8 +1809,12 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     ar.q_tiles = d_fqt; ar.Q = d_fq; ar.n_q = n_fail; ar.active = nullptr; ar.theta = d_ftheta;
                     ar.n_split = (int)rs; ar.cbuf = d_rbuf; ar.cap = rcap;
                     ar.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_rbuf) + nb);
-                    if ((rc = quad ? launch_quad<false>(ctx, ar, fg, rs, st) : launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st)))
-                        return rc;
+                    if (quad)
+                        rc = compact ? launch_quad<false, true>(ctx, ar, fg, rs, st) : launch_quad<false>(ctx, ar, fg, rs, st);
+                    else
+                        rc = compact ? launch_scan<MODE_COLLECT, false, 1, true>(ctx, ar, fg, rs, st)
+                                     : launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st);
+                    if (rc) return rc;
                     const int parts = 4 * (int)rs;
                     const size_t fin_smem = (size_t)kFinWarps * parts * rcap * sizeof(unsigned long long);
                     if (fin_smem > 48 * 1024)
@@ -1724,12 +1844,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         const uint4 *d_in_t = d_fqt;
                         if (d_list2) {
                             const long long fp2 = (n_fail2 + kQPair - 1) / kQPair;
-                            pack_f16_tiles_kernel<<<grid_for(ctx, fp2 * 2 * kDTile * 2), 256, 0, st>>>(d_fq2, n_fail2, fp2 * 2, d_fqt2, 1);
-                            FWAV_LAUNCH_CHECK(ctx);
+                            if ((rc = pack(d_fq2, n_fail2, fp2 * 2, d_fqt2, 1, 0))) return rc;
                             d_in_t = d_fqt2;
                         }
                         rc = launch_lists(ctx, d_in_t, d_et, d_in, d_emb, n_fail2, n_d, (int)n_stages, top_k, nullptr,
-                                          d_list2 ? d_fc2 : d_fc, d_list2 ? d_fs2 : d_fs, dbg, st);
+                                          d_list2 ? d_fc2 : d_fc, d_list2 ? d_fs2 : d_fs, dbg, st, compact);
                     } else {
                         rc = fwav_launch_topk_ffma(ctx, d_in, n_fail2, d_emb, n_d, ED, top_k, nullptr, d_list2 ? d_fc2 : d_fc,
                                                    d_list2 ? d_fs2 : d_fs, st);

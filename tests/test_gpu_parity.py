@@ -535,6 +535,42 @@ def test_experimental_four_buffer_collect(ctx, monkeypatch, n_q, top_k, mode):
     assert np.array_equal(bits(out["umma"][1]), bits(out["ffma"][1]))
 
 
+@pytest.mark.skipif(os.environ.get("FWAV_TEST_EXPERIMENTAL") != "1",
+                    reason="compact split (FWAV_UMMA_COMPACT=1) was written after round 1's GPU budget was spent: "
+                           "not yet run on a device; set FWAV_TEST_EXPERIMENTAL=1 to try it")
+@pytest.mark.parametrize("n_q,top_k,mode,quad", [(777, 32, "precise", "0"), (777, 32, None, "0"), (3000, 64, None, "0"),
+                                                 (3000, 64, "precise", "1"), (300, 32, "lists", "0")])
+def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
+    """Embeddings shaped like range_size 4 (3 live tonal + 4 live transient dimensions, the rest exactly zero):
+    the two-MMA compact split must return what the FFMA kernel returns."""
+    monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
+    monkeypatch.setenv("FWAV_UMMA_QUAD", quad)
+    if mode:
+        monkeypatch.setenv("FWAV_UMMA_MODE", mode)
+    ED = 16
+    n_d = (1 << 17) + 77
+    rng = np.random.default_rng(400 + n_q)
+    e = np.zeros((n_d, ED), np.float32)
+    e[:, 0:3] = rng.standard_normal((n_d, 3))
+    e[:, 8:12] = rng.standard_normal((n_d, 4))
+    for h in (slice(0, 8), slice(8, 16)):
+        e[:, h] /= np.linalg.norm(e[:, h], axis=1, keepdims=True)
+    q = np.ascontiguousarray(e[rng.choice(n_d, n_q, replace=False)])
+    q[:, [0, 1, 2, 8, 9, 10, 11]] += (rng.standard_normal((n_q, 7)) * 0.05).astype(np.float32)
+    d_e, d_q = ctx.upload(e), ctx.upload(q)
+    out = {}
+    for impl in ("ffma", "umma"):
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * top_k * 4), ctx.alloc(n_q * top_k * 4)
+        try:
+            ctx.topk(d_q.ptr, n_q, d_e.ptr, n_d, ED, top_k, None, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32))
+    assert np.array_equal(out["umma"][0], out["ffma"][0])
+    assert np.array_equal(bits(out["umma"][1]), bits(out["ffma"][1]))
+
+
 def test_config2_full_size_sample(ctx):
     """BASELINE.json config 2 at FULL size (180 s / 44.1 kHz, 496 125 ranges x 1 983 477 domains) through the
     host-buffer C ABI; a seeded sample of ranges is checked against the oracle: brute-force float32 search over the
