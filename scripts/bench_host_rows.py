@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Host-side rows of SURVEY.md §8(f) (N1 container, N2 pre-step, N3 match hand-off) at config-2 size,
 timed next to the reference's own functions.  CPU only; needs /root/reference (build container), so it is a
-measurement script, not part of bench.py.  TEST/MEASUREMENT INFRASTRUCTURE: imports the reference through
-oracle/make_golden.load_reference.
+measurement script, not part of bench.py, and it never runs on the GPU box.  The reference is imported unmodified
+under a results-neutral `librosa` stub (its module-level import is never used on these paths).
 
     OMP_NUM_THREADS=1 python scripts/bench_host_rows.py [--scale 1.0] > profiles/r01_host_rows.json
 
@@ -13,10 +13,26 @@ import argparse, hashlib, json, os, sys, tempfile, time
 
 os.environ.setdefault("OMP_NUM_THREADS", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "audio-compression_b200"))
 import numpy as np  # noqa: E402
 from fwav_b200 import container, prestep, synth  # noqa: E402
+
+
+def load_reference():
+    import logging, types
+    stub = types.ModuleType("librosa")
+    stub.filters = types.ModuleType("librosa.filters")
+    stub.filters.mel = lambda sr, n_fft, n_mels=40, fmin=0, fmax=None: np.zeros((n_mels, n_fft // 2 + 1), np.float32)
+    sys.modules["librosa"], sys.modules["librosa.filters"] = stub, stub.filters
+    sys.path.insert(0, "/root/reference")
+    ours = sys.modules.pop("fractal", None)          # the drop-in has the same module name
+    import fractal as ref
+    sys.modules.pop("fractal", None)
+    if ours is not None:
+        sys.modules["fractal"] = ours
+    logging.getLogger().setLevel(logging.WARNING)
+    ref.logger.setLevel(logging.WARNING)
+    return ref
 
 
 def best_of(fn, reps):
@@ -42,7 +58,6 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
-    from oracle.make_golden import load_reference
     ref = load_reference()
 
     rate, tile = 44100, 4096
