@@ -163,3 +163,16 @@ def test_api_surface_matches_reference():
                  "process_file_compress", "process_file_decompress", "main", "voiced_detection"):
         assert callable(getattr(fractal, name))
     assert (fractal.top_k, fractal.EMBED_K, fractal.FWAV_VERSION) == (32, 32, 1)
+
+
+def test_experimental_collect_protocol_simulation():
+    """The mbarrier protocol of the (not yet device-tested) four-buffer collect kernel, as modelled in
+    scripts/sim/quad_protocol_sim.py: random schedules must finish without deadlock or early overwrite."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "sim", "quad_protocol_sim.py")
+    spec = importlib.util.spec_from_file_location("quad_protocol_sim", path)
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for n_visit in (2, 6, 34, 70):
+        for seed in range(4):
+            sim.run(n_visit, seed)
