@@ -233,5 +233,21 @@ def main():
     print("golden bytes:", total)
 
 
+def main_t2048():
+    """Added after the first batch (the other fixtures are left untouched): tile 2048 -> N=8, ds=2, the one
+    constant-bank geometry (4 / 8 / 16) the first batch did not cover."""
+    from fwav_b200 import synth
+    ref = load_reference()
+    sig = synth.music_like(seconds=0.6, rate=22050, seed=21)
+    g = replay(ref, sig, 2048)
+    assert int(g["range_size"]) == 8 and int(g["domain_step"]) == 2
+    add_decodes(ref, g, DECODES)
+    np.savez_compressed(os.path.join(GOLD, "music_t2048.npz"), **g)
+    print("music_t2048: ranges", len(g["idx"]), "domains", len(g["domains"]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "t2048":
+        main_t2048()
+    else:
+        main()

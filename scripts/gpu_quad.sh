@@ -5,6 +5,8 @@ mkdir -p gpurun_out; rm -f gpurun_out/quad.txt
 FWAV_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "experimental" 2>&1 | tail -5 > gpurun_out/quad_tests.txt
 cat gpurun_out/quad_tests.txt
 grep -q "passed" gpurun_out/quad_tests.txt || exit 1
+# the N=8 fixture that has not been on a device yet (tile 2048)
+FWAV_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "music_t2048" 2>&1 | tail -4
 for quad in 0 1; do
   echo "== FWAV_UMMA_QUAD=$quad (config 2)" >> gpurun_out/quad.txt
   FWAV_UMMA_QUAD=$quad FWAV_UMMA_VERBOSE=1 timeout 200 python scripts/time_topk.py 1.0 umma 3 > gpurun_out/quad_run.out 2> gpurun_out/quad_run.err

@@ -54,7 +54,7 @@ def test_product_never_imports_the_oracle():
                 assert "fwav_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
 
 
-@pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024", "music_t3000"])
+@pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024", "music_t3000", "music_t2048"])
 def test_prestep_matches_reference(name):
     from fwav_b200.prestep import frame_ranges
     g = golden(name)

@@ -9,7 +9,7 @@ from host_harness import Harness
 
 H = Harness()
 ALL = ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024",
-       "music_k64", "tiny_kfull", "sine_t1100", "music_t3000"]
+       "music_k64", "tiny_kfull", "sine_t1100", "music_t3000", "music_t2048"]
 
 
 def bits(a):
@@ -57,7 +57,7 @@ def test_affine_bit_exact_given_candidates(name):
 
 
 @pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024",
-                                  "float_t1024", "sentinel_decode", "music_t3000"])
+                                  "float_t1024", "sentinel_decode", "music_t3000", "music_t2048"])
 def test_decode_bit_exact(name):
     g = golden(name)
     N = int(g["range_size"])

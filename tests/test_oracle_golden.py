@@ -7,7 +7,7 @@ from conftest import golden
 from oracle import fwav_oracle as O
 
 REPLAYS = ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024",
-           "music_k64", "tiny_kfull", "sine_t1100", "music_t3000"]
+           "music_k64", "tiny_kfull", "sine_t1100", "music_t3000", "music_t2048"]
 
 
 def bits(a):
@@ -33,7 +33,7 @@ def test_compress_replay_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024",
-                                  "float_t1024", "sentinel_decode"])
+                                  "float_t1024", "sentinel_decode", "music_t2048"])
 def test_decode_bit_exact(name):
     g = golden(name)
     n_ranges = len(g["idx"])
