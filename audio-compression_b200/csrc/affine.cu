@@ -35,7 +35,7 @@ __device__ __forceinline__ bool better(float e1, int p1, float e2, int p2) {
 template <int NT>
 __global__ void __launch_bounds__(256, NT == 16 ? 3 : 1)
 affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
-              const float *__restrict__ domains, const int32_t *__restrict__ cand, int K, float clipf,
+              const float *__restrict__ domains, long long n_d, const int32_t *__restrict__ cand, int K, float clipf,
               int32_t *__restrict__ o_idx, float *__restrict__ o_s, float *__restrict__ o_o,
               uint8_t *__restrict__ o_sym, float *__restrict__ o_err) {
     const int lane = threadIdx.x & 31;
@@ -61,7 +61,8 @@ affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
         for (int c0 = 0; c0 < K; c0 += 32) {
             const int c = c0 + lane;
             if (c < K) {
-                const int raw = __ldg(cand + i * K + c);
+                int raw = __ldg(cand + i * K + c);
+                if (raw >= n_d) raw = -1;                             // caller-supplied table: never read past the domains
                 const int d = raw < 0 ? 0 : raw;                      // :772-773
                 const float *tp = domains + (long long)d * N;
                 float treg[NT > 0 ? NT : 1];
@@ -122,7 +123,7 @@ int fwav_launch_affine(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N,
     const int grid = (int)(need < cap ? need : cap);
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_ranges) | reinterpret_cast<uintptr_t>(d_domains)) & 15) == 0;
 #define FWAV_AFFINE(NT)                                                                          \
-    affine_kernel<NT><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, d_cand, K, clipf, d_idx, \
+    affine_kernel<NT><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, (long long)n_d, d_cand, K, clipf, d_idx, \
                                             d_s, d_o, d_sym, d_err)
     if (aligned && N == 4) FWAV_AFFINE(4);
     else if (aligned && N == 8) FWAV_AFFINE(8);

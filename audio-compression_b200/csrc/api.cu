@@ -320,24 +320,32 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, 
         FWAV_CUDA(ctx, cudaMemcpyAsync(h_domains, d_domains, sizeof(float) * (size_t)n_dom * N, cudaMemcpyDeviceToHost,
                                        ctx->copy_stream));
     }
-    if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return rc;
+    // Once the download has been queued the caller's h_domains is in flight: every exit below goes through
+    // `finish`, which waits for the copy stream before the buffer can be freed or reused.
+    auto finish = [&](int code) -> int {
+        if (h_domains) {
+            const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+            if (e != cudaSuccess && code == FWAV_OK)
+                code = fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the domain table failed: %s", cudaGetErrorString(e));
+        }
+        return code;
+    };
+    if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return finish(rc);
     rc = fwav_compress_device(ctx, d_signal, n_samples, d_ranges, n_ranges, 0, tile_size, emb_dim, top_k,
                               energy_thresh, fast_mode, query_mode, 0, d_domains, d_emb, d_idx, d_s, d_o,
                               d_sym, d_err, st);
-    if (rc) {
-        if (h_domains) cudaStreamSynchronize(ctx->copy_stream);
-        return rc;
-    }
+    if (rc) return finish(rc);
+    cudaError_t ce = cudaSuccess;
     if (n_ranges) {
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_idx, d_idx, nr * 4, cudaMemcpyDeviceToHost, st));
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_s, d_s, nr * 4, cudaMemcpyDeviceToHost, st));
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_o, d_o, nr * 4, cudaMemcpyDeviceToHost, st));
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, nr * 4, cudaMemcpyDeviceToHost, st));
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_sym, d_sym, nr, cudaMemcpyDeviceToHost, st));
+        const struct { void *h; const void *d; size_t n; } out[5] = {
+            {h_idx, d_idx, nr * 4}, {h_s, d_s, nr * 4}, {h_o, d_o, nr * 4}, {h_err, d_err, nr * 4}, {h_sym, d_sym, nr}};
+        for (const auto &o : out)
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(o.h, o.d, o.n, cudaMemcpyDeviceToHost, st);
     }
-    FWAV_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_domains) FWAV_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    return FWAV_OK;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess)
+        return finish(fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the matches failed: %s", cudaGetErrorString(ce)));
+    return finish(FWAV_OK);
 }
 
 int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains, const int32_t *h_idx,
@@ -351,6 +359,10 @@ int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains, c
     if (n_ranges == 0) return FWAV_OK;
     FWAV_REQUIRE(ctx, h_domains && h_idx && h_s && h_o && h_sym && h_out, "null buffer");
     FWAV_REQUIRE(ctx, n_domains >= 1, "decoder needs at least one domain row");
+    // a corrupt or forged container must not index past the table (the reference raises IndexError, fractal.py:1414)
+    for (int64_t i = 0; i < n_ranges; ++i)
+        FWAV_REQUIRE(ctx, h_idx[i] < n_domains, "index out of bounds: match %lld points at domain %d of %lld",
+                     (long long)i, h_idx[i], (long long)n_domains);
     const int N = range_size;
     float *d_domains, *d_out;
     unsigned char *d_match;

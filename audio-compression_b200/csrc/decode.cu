@@ -27,7 +27,7 @@ struct DecodeState {
     int iters_run;
     int done;
     float delta;
-    int pad;
+    int bad_index;     // some match pointed past the domain table (the reference raises IndexError, fractal.py:1414)
 };
 
 template <int NT>
@@ -36,13 +36,17 @@ decode_iter_kernel(const float *__restrict__ domains, const int32_t *__restrict_
                    const float *__restrict__ s_st, const float *__restrict__ o_st,
                    const uint8_t *__restrict__ sym, long long n_r, int N, float clipf, int damped,
                    float one_minus_damp, float damp, int first, const float *__restrict__ cur,
-                   float *__restrict__ nxt, const DecodeState *__restrict__ state,
-                   double *__restrict__ partials) {
+                   float *__restrict__ nxt, DecodeState *__restrict__ state,
+                   double *__restrict__ partials, long long n_d) {
     if (state->done) return;
     double dsq = 0.0, csq = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_r;
          i += (long long)gridDim.x * blockDim.x) {
-        const int raw = __ldg(idx + i);
+        int raw = __ldg(idx + i);
+        if (raw >= n_d) {            // corrupt or forged container: never read past the table; reported by the host side
+            state->bad_index = 1;
+            raw = -1;
+        }
         const bool dead = raw < 0;                                        // :1399-1426
         const bool flip = !dead && __ldg(sym + i) != 0;
         const float sv = dead ? 0.0f : __ldg(s_st + i);
@@ -181,7 +185,7 @@ int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, 
                            reinterpret_cast<uintptr_t>(d_next)) & 15) == 0;
 #define FWAV_DEC(NT)                                                                                   \
     decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
-                                                      damped, omd, dmp, first, d_cur, d_next, d_state, d_part)
+                                                      damped, omd, dmp, first, d_cur, d_next, d_state, d_part, (long long)n_d)
     if (aligned && N == 4) FWAV_DEC(4);
     else if (aligned && N == 8) FWAV_DEC(8);
     else if (aligned && N == 16) FWAV_DEC(16);
@@ -234,7 +238,7 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
         float *nxt = buf[(it + 1) & 1];
 #define FWAV_DEC(NT)                                                                               \
     decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
-                                                      damped, omd, dmp, it == 0, cur, nxt, d_state, d_part)
+                                                      damped, omd, dmp, it == 0, cur, nxt, d_state, d_part, (long long)n_d)
         if (aligned && N == 4) FWAV_DEC(4);
         else if (aligned && N == 8) FWAV_DEC(8);
         else if (aligned && N == 16) FWAV_DEC(16);
@@ -257,5 +261,6 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
     FWAV_CUDA(ctx, cudaStreamSynchronize(st));
     if (iters_run) *iters_run = h.iters_run;
     if (last_delta) *last_delta = h.delta;
+    FWAV_REQUIRE(ctx, !h.bad_index, "index out of bounds: a match points past the %lld-row domain table", (long long)n_d);
     return FWAV_OK;
 }

@@ -1171,6 +1171,221 @@ __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kerne
     }
 }
 
+// ---------------------------------------------------------------------------
+// collect_fat_kernel: the hi*hi-only collect pass with FOUR 128-column accumulator buffers and EIGHT "fat"
+// epilogue warps (two per scheduler), the round-2 layout of the dominant kernel.
+//
+// What bounded scan_kernel<MODE_COLLECT, true, 1>: (a) ~40 instructions of waiting, addressing and
+// loop control per warp and stage against 36-72 max instructions, on the same ALU pipe; (b) with 96 registers a
+// warp holds two 32-column chunks, so a 256-column buffer is held for two rounds of load + reduce before it goes
+// back to the MMA thread, and TMEM has room for two such buffers only (Little's law on 512 columns).  Here
+//   * a tile is 128 domains (M128 N128 K16: 136 cycles, 272 per 256 columns -- below the ALU floor of the
+//     reduction), so TMEM holds four accumulators and a set of warps always finds its next one ready;
+//   * warp = (TMEM lane quadrant, set); set s owns the tiles t = s (mod 2), i.e. buffers s and s + 2, and a warp
+//     reads ALL 128 columns of an own tile with two tcgen05.ld x64 (128 data registers, 352 threads per CTA);
+//     the buffer goes back as soon as the second load has landed: before anything is reduced;
+//   * the loads are software-pipelined across tiles: columns 0-63 of the next own tile travel while columns
+//     64-127 of this one are reduced, columns 64-127 while its columns 0-63 are;
+//   * per warp and tile: two mbarrier operations, two loads, 2 x 33 max/compare instructions.
+// Hits (a score >= the row's threshold) are staged eight at a time in shared memory and leave as whole 32-byte
+// sectors, so L2 never has to fetch a sector from DRAM to merge a 4-byte store into it (round 1: 6.1 GB of such
+// reads per launch).  A thread's list is the two parts (2 * set, 2 * set + 1) of the row's candidate buffer, laid
+// end to end; finalize_kernel reads the parts as before.
+// ---------------------------------------------------------------------------
+constexpr int kFatEpi = 8;
+constexpr int kFatThreads = (kFatEpi + 3) * 32;
+constexpr uint32_t kFatOffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
+constexpr uint32_t kFatSmem = kFatOffStage + kFatEpi * 8 * 32 * 4;
+
+// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : FWAV_R32(v), FWAV_R32(w)
+        : "r"(taddr)
+        : "memory");
+}
+
+template <bool HI>
+__global__ void __launch_bounds__(kFatThreads, 1) collect_fat_kernel(const ScanArgs a) {
+    constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_q = a.n_q;
+    const uint8_t *__restrict__ active = a.active;
+    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
+    const long long q_base = (long long)group_id * kQTile;
+    const uint32_t bars = smem_u32(smem + kQuadOffBars);
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQuadRing, bar_tfull = bars + 16 * kQuadRing,
+                   bar_tempty = bar_tfull + 32, bar_a = bar_tempty + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQuadOffBars + 16 * kQuadRing + 80);
+
+    {   // energy-pruned stretch: nothing to scan
+        int any = 0;
+        for (int i = threadIdx.x; i < kQTile; i += kFatThreads) {
+            const long long q = q_base + i;
+            if (q < n_q && (!active || active[q])) any = 1;
+        }
+        if (!__syncthreads_or(any)) {
+            for (int i = threadIdx.x; i < kQTile; i += kFatThreads) {
+                const long long q = q_base + i;
+                if (q < n_q)
+                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kQuadRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kFatEpi / 2); }
+        mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kFatEpi) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // this CTA's share of the table, in 128-domain tiles; the scan starts at the CTA's own rows and wraps around
+    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
+    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;
+    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
+
+    if (warp == kFatEpi) {
+        // ===== producer: one bulk copy per tile ([hi | lo] is contiguous in the packed table) =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, kOpBytes);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kOpBytes, bar_a);
+            int tt = t_first;
+            for (int t = 0; t < n_visit; ++t) {
+                const int s = t & (kQuadRing - 1);
+                mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / kQuadRing) & 1) ^ 1));
+                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
+                bulk_g2s(smem_u32(smem + kQuadOffRing + s * kTileBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kOpBytes,
+                         bar_full + 8 * s);
+                if (++tt == t_hi) tt = t_lo;
+            }
+        }
+    } else if (warp > kFatEpi) {
+        // ===== two MMA issuers: thread i owns the tiles t = i (mod 2), i.e. buffers i and i + 2 =====
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            const uint32_t a_hi = smem_u32(smem + kOffA);
+            const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_hi + kPartBytes);
+            for (int t = warp - (kFatEpi + 1); t < n_visit; t += 2) {
+                const int s = t & (kQuadRing - 1), buf = t & 3;
+                const uint32_t b_hi = smem_u32(smem + kQuadOffRing + s * kTileBytes);
+                const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_hi + kPartBytes);
+                const uint32_t d = tmem_base + (uint32_t)(buf * kDTile);
+                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQuadRing) & 1));
+                mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((t >> 2) & 1) ^ 1));
+                tc_fence_after();
+                if (HI) {
+                    umma_f16_m128n128(d, da_hi, db_hi, 0);
+                } else {
+                    umma_f16_m128n128(d, da_hi, db_lo, 0);
+                    umma_f16_m128n128(d, da_lo, db_hi, 1);
+                    umma_f16_m128n128(d, da_hi, db_hi, 1);
+                }
+                umma_commit<1>(bar_tfull + 8 * buf);
+                umma_commit<1>(bar_empty + 8 * s);
+            }
+        }
+    } else {
+        // ===== epilogue: one query row per thread; warp = (lane quadrant, set) =====
+        const int quad = warp & 3, set = warp >> 2;
+        const long long q = q_base + quad * 32 + lane;
+        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
+        const int cap2 = 2 * a.cap;                             // this thread's list: parts 2 * set and 2 * set + 1
+        int32_t *list = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + 2 * set) * (long long)a.cap;
+        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kFatOffStage) + warp * 256 + lane;    // slot k: stg[32 * k]
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        int cnt = 0;
+        // eight staged indices -> one 32-byte sector of the list
+        auto flush = [&](int at) {
+            const uint4 lo4 = make_uint4(stg[0], stg[32], stg[64], stg[96]);
+            const uint4 hi4 = make_uint4(stg[128], stg[160], stg[192], stg[224]);
+            uint4 *dst = reinterpret_cast<uint4 *>(list + at);
+            dst[0] = lo4;
+            dst[1] = hi4;
+        };
+        auto push = [&](int id) {
+            stg[(cnt & 7) * 32] = (uint32_t)id;
+            if ((cnt & 7) == 7 && cnt < cap2) flush(cnt - 7);
+            ++cnt;
+        };
+        // rare path (0.4 % of a thread's chunks): which columns pass goes into a bit mask first, so that the store
+        // sequence exists once per chunk and the loop body stays within the instruction cache
+        auto look = [&](const uint32_t (&x)[32], int col) {
+            if (chunk_max(x) >= tau) {
+                unsigned mask = 0u;
+                for_each_ge(x, tau, [&](int j) { mask |= 1u << j; });
+                while (mask) {
+                    push(col + __ffs(mask) - 1);
+                    mask &= mask - 1;
+                }
+            }
+        };
+        const int n_own = (n_visit - set + 1) / 2;               // tiles set, set + 2, ... below n_visit
+        if (n_own > 0) {
+            uint32_t p0[32], p1[32], r0[32], r1[32];             // columns 0-63 and 64-127 of the tile in hand
+            int tt = t_first + set;
+            if (tt >= t_hi) tt -= n_visit;
+            mbar_wait(bar_tfull + 8 * set, 0);
+            tc_fence_after();
+            tmem_ld64(t_lane + (uint32_t)(set * kDTile), p0, p1);
+            tmem_wait_ld2(p0, p1);
+            tmem_ld64(t_lane + (uint32_t)(set * kDTile) + 64, r0, r1);
+            for (int i = 0; i < n_own; ++i) {
+                const int buf = set + 2 * (i & 1);
+                const int col = tt * kDTile;
+                tt += 2;
+                if (tt >= t_hi) tt -= n_visit;
+                look(p0, col);
+                look(p1, col + 32);
+                tmem_wait_ld2(r0, r1);
+                // the whole tile is in registers: hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
+                const bool more = i + 1 < n_own;
+                const int nbuf = set + 2 * ((i + 1) & 1);
+                if (more) {
+                    mbar_wait(bar_tfull + 8 * nbuf, (uint32_t)(((i + 1) >> 1) & 1));
+                    tc_fence_after();
+                    tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile), p0, p1);
+                }
+                look(r0, col + 64);
+                look(r1, col + 96);
+                if (more) {
+                    tmem_wait_ld2(p0, p1);
+                    tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile) + 64, r0, r1);
+                }
+            }
+        }
+        if ((cnt & 7) && cnt < cap2) flush(cnt & ~7);            // the last, partial sector (the count says how much of it is valid)
+        if (q < n_q) {
+            const int c0 = cnt < a.cap ? cnt : a.cap;
+            int *cc = a.ccount + (q * a.n_split + split) * 4 + 2 * set;
+            cc[0] = c0;
+            cc[1] = cnt - c0;                                    // above cap: finalize_kernel reads it as an overflow
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kFatEpi) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core score - canonical float32 score| (measured max 3.9e-7)
 // hi*hi term alone: inputs rounded to fp16 (relative 2^-11 each), sum |q_k e_k| <= |q||e| <= 2 (two unit heads):
 // 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
@@ -1431,6 +1646,7 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
+constexpr bool kDefaultFat = false;           // default layout of the hi*hi-only collect pass (see FWAV_UMMA_COLLECT)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
 inline int grid_for(const fwav_ctx *ctx, long long work) {
@@ -1442,11 +1658,8 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
 template <int MODE, bool HI, int CG, bool COMPACT = false>
 int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
     constexpr int smem = (int)smem_bytes(MODE, CG);
-    static bool attr_set = false;          // per process; the attribute is per function, not per context
-    if (!attr_set) {
-        FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    // function attributes are per device: set before every launch (a process may hold contexts on several GPUs)
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     scan_kernel<MODE, HI, CG, COMPACT><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
@@ -1455,12 +1668,17 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
 // the experimental four-buffer collect pass (FWAV_UMMA_QUAD=1): one CTA per 128 queries and table share
 template <bool HI, bool COMPACT = false>
 int launch_quad(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
-        attr_set = true;
-    }
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
     collect_quad_kernel<HI, COMPACT><<<(unsigned)(groups * split), n_threads(MODE_COLLECT), kQuadSmem, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
+// the fat-warp four-buffer collect pass (hi*hi-only; see collect_fat_kernel): one CTA per 128 queries and table share
+template <bool HI>
+int launch_fat(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_fat_kernel<HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFatSmem));
+    collect_fat_kernel<HI><<<(unsigned)(groups * split), kFatThreads, kFatSmem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1569,8 +1787,12 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     };
     if ((rc = pack(d_emb, n_d, e_tiles, d_et, 1, 1))) return rc;
     if ((rc = pack(d_q, n_q, q_tiles, d_qt, 1, 0))) return rc;
-    const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are wrong when set)
+#ifdef FWAV_DEBUG_KNOBS
+    const char *dbg_env = getenv("FWAV_UMMA_DEBUG");   // profiling aid (results are WRONG when set): debug builds only
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+    const int dbg = 0;
+#endif
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
     const bool fast = n_d >= kFastMinDomains && (top_k > 32 || !(mode_env && !strcmp(mode_env, "lists")));
     ctx->search_fast_path = fast;
@@ -1601,9 +1823,17 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = pack(d_emb, n_d, s_stages * 2, d_es, sample_stride, 1))) return rc;
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
-    const char *quad_env = getenv("FWAV_UMMA_QUAD");          // experimental four-buffer collect pass (see collect_quad_kernel)
-    const bool quad = single && quad_env && atoi(quad_env) == 1;
-    const long long batch = n_q < kBatchQueries ? n_q : kBatchQueries;
+    // layout of the hi*hi-only collect pass: "fat" (collect_fat_kernel), "sets" (scan_kernel, two epilogue sets),
+    // "quad" (collect_quad_kernel); every layout returns the same candidates
+    const char *layout_env = getenv("FWAV_UMMA_COLLECT");
+    const bool quad = single && layout_env && !strcmp(layout_env, "quad");
+    const bool fat = single && !quad && (layout_env ? !strcmp(layout_env, "fat") : kDefaultFat);
+    long long batch_cap = kBatchQueries;
+    if (const char *batch_env = getenv("FWAV_UMMA_BATCH")) {  // test knob: small batches exercise the multi-batch loop
+        const long long v = atoll(batch_env);
+        if (v >= kQPair) batch_cap = v / kQPair * kQPair;
+    }
+    const long long batch = n_q < batch_cap ? n_q : batch_cap;
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
     int *d_cnt = nullptr, *d_fail = nullptr;
@@ -1613,7 +1843,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
     if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
         const int v = atoi(cap_env);
-        if (v >= 2 && v <= collect_cap) collect_cap = v & ~1;
+        if (v >= 16 && v <= collect_cap) collect_cap = v & ~15;    // parts stay whole 32-byte sectors, halved too
     }
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * collect_cap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
@@ -1707,7 +1937,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
-            if (quad)
+            if (fat && hi_only)
+                rc = launch_fat<true>(ctx, ax, g, sp, st);
+            else if (quad)
                 rc = hi_only ? launch_quad<true>(ctx, ax, g, sp, st)
                    : compact ? launch_quad<false, true>(ctx, ax, g, sp, st) : launch_quad<false>(ctx, ax, g, sp, st);
             else if (compact && !hi_only)
@@ -1719,22 +1951,20 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             if (rc) return rc;
         }
         if ((rc = mark(ctx, slot, 3, st))) return rc;
-        if (dbg & 64) {
+#ifdef FWAV_DEBUG_KNOBS
+        if (dbg & 64) {      // clock64 stamps of CTA 0, printed to stderr (debug builds only; no file I/O in the library)
             static long long h_trace[kTraceStages * 8];
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_trace, a.trace, sizeof h_trace, cudaMemcpyDeviceToHost, st));
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
-            FILE *f = fopen("gpurun_out/umma_trace.txt", "w");
-            if (f) {
-                fprintf(f, "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
-                const long long t0 = h_trace[0];
-                for (int i = 0; i < kTraceStages; ++i) {
-                    fprintf(f, "%4d:", kTraceFrom + i);
-                    for (int k = 0; k < 8; ++k) fprintf(f, " %8lld", h_trace[i * 8 + k] ? h_trace[i * 8 + k] - t0 : -1ll);
-                    fprintf(f, "\n");
-                }
-                fclose(f);
+            fprintf(stderr, "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
+            const long long t0 = h_trace[0];
+            for (int i = 0; i < kTraceStages; ++i) {
+                fprintf(stderr, "%4d:", kTraceFrom + i);
+                for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h_trace[i * 8 + k] ? h_trace[i * 8 + k] - t0 : -1ll);
+                fprintf(stderr, "\n");
             }
         }
+#endif
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long qoff = part ? main_q : 0;

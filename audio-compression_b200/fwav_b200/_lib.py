@@ -183,6 +183,8 @@ class Context:
             text = msg.decode("utf-8", "replace") if msg else ""
             if rc == -1 and text.startswith("mmap length is greater than file size"):
                 raise ValueError(text)      # what np.memmap raises in the reference (fractal.py:1190)
+            if rc == -1 and text.startswith("index out of bounds"):
+                raise IndexError(text)      # what the reference's fancy index raises (fractal.py:1414)
             raise FwavError(f"fwav error {rc}: {text}")
 
     # ---- control ----
@@ -256,6 +258,14 @@ class Context:
         domains = _as(domains, np.float32)
         idx, s, o, sym = _as(idx, np.int32), _as(s, np.float32), _as(o, np.float32), _as(sym, np.uint8)
         n_r = len(idx)
+        # what the reference's numpy indexing would reject (fractal.py:1391-1414) must not reach the device
+        if domains.ndim != 2 or domains.shape[1] != int(range_size):
+            raise ValueError(f"domains must be (n_domains, {int(range_size)}), got {domains.shape}")
+        if not (len(s) == len(o) == len(sym) == n_r):
+            raise ValueError(f"match arrays differ in length: idx {n_r}, s {len(s)}, o {len(o)}, sym {len(sym)}")
+        if n_r and int(idx.max()) >= domains.shape[0]:
+            raise IndexError(f"index out of bounds: match {int(idx.argmax())} points at domain {int(idx.max())} "
+                             f"of {domains.shape[0]}")
         if out is None:
             out = np.empty(n_r * range_size, np.float32)
         it, delta = C.c_int(0), C.c_float(0)

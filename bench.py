@@ -107,15 +107,24 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- workload
 def make_workload(scale=1.0):
-    from fwav_b200 import _lib, synth
+    """Synthetic signal + framed ranges.  Pure numpy (fwav_b200.synth / prestep): the reference arm calls this too
+    and must not load libfwav_b200.so."""
+    from fwav_b200 import synth
     from fwav_b200.prestep import frame_ranges
     sig, rate, tile, k = synth.make(WORKLOAD, scale)
-    globals()["_WL_SECONDS"] = synth.CONFIGS[WORKLOAD][1]["seconds"] * scale
-    N, ds = _lib.geometry(tile)
+    N = max(4, tile // 256)                       # fractal.py:1070
+    ds = max(1, N // 4)                           # fractal.py:1071
     ranges, original_len = frame_ranges(sig, N, ENERGY_THRESH)
-    n_d = _lib.count_domains(len(sig), tile, ds)
+    n_d = (len(sig) - tile) // ds + 1 if len(sig) >= tile else 0      # fractal.py:297-304
     return dict(signal=sig, rate=rate, tile=tile, top_k=k, N=N, ds=ds, ranges=ranges, n_samples=len(sig),
                 n_ranges=len(ranges), n_domains=n_d, original_len=original_len)
+
+
+def config_dict(w, scale, world):
+    """The `config` object of the JSON line: identical keys and values in both arms (the driver compares them)."""
+    return {"workload": workload_name(w, scale), "n_samples": int(w["n_samples"]), "n_ranges": int(w["n_ranges"]),
+            "n_domains": int(w["n_domains"]), "pairs": float(w["n_ranges"]) * float(w["n_domains"]),
+            "top_k": int(w["top_k"]), "emb_dim": EMB_DIM, "query_mode": "reference (q_i = E[i])"}
 
 
 def workload_name(w, scale):
@@ -455,15 +464,14 @@ def run_ours(args):
         "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(w, args.scale), "n_samples": n, "n_ranges": n_r,
-                   "n_domains": n_d, "pairs": pairs, "top_k": K, "emb_dim": EMB_DIM,
-                   "query_mode": "reference (q_i = E[i])",
-                   "search_impl": ("tcgen05 (cta_group::1, M128 N256 K16) fp16 hi/lo split, 128x256 tiles per CTA: threshold pass over a strided "
-                                   "sample (3 MMAs/tile), collect pass (hi*hi term alone when the probe after pass 1 allows it, else "
-                                   "3 MMAs/tile), exact float32 finalize with per-query verification, second tensor-core pass "
-                                   "then exact list/FFMA kernel for queries that fail it" if tensor else "FP32 FFMA"),
-                   "parallelism": f"ranges sharded x{world}" + (", tables NCCL-broadcast from rank 0, matches all-gathered" if world > 1 else ""),
-                   "l2": "flushed between timed steps (256 MiB device write outside the event pairs)"},
+        "config": config_dict(w, args.scale, world),
+        "details": {"search_impl": ("tcgen05 (cta_group::1) fp16 hi/lo split: threshold pass over a strided sample "
+                                    "(M128 N256 K16, 3 MMAs/tile), collect pass (hi*hi term alone, M128 N128 K16 into four "
+                                    "accumulator buffers, when the probe after pass 1 allows it; else 3 MMAs/tile), exact "
+                                    "float32 finalize with per-query verification, second tensor-core pass then exact "
+                                    "list/FFMA kernel for queries that fail it" if tensor else "FP32 FFMA"),
+                    "parallelism": f"ranges sharded x{world}" + (", matches all-gathered" if world > 1 else ""),
+                    "l2": "flushed between timed steps (256 MiB device write outside the event pairs)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "kernels": kern, "decode": decode,
         "peaks": peaks,
@@ -624,8 +632,7 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": n_steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * w["n_ranges"] / v, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(w, args.scale), "n_ranges": w["n_ranges"],
-                       "n_domains": w["n_domains"], "top_k": w["top_k"], "emb_dim": EMB_DIM},
+            "config": config_dict(w, args.scale, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": details,
             "e2e": {"value": v, "unit": "ranges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -31,6 +31,7 @@ struct Params {
     int ld_iters;
     int ld_mode;          // 0: loads only, 1: + 3-input max tree and threshold compare
     int sync_mode;        // 1: MMA thread and LDTM warps hand accumulator buffers over through mbarriers
+    int tf32;             // 1: kind::tf32 (K = 8 per instruction, same 32-byte operand rows) instead of kind::f16 (K = 16)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,6 +74,11 @@ __device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a, uint64_t b, uint
     else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// kind::tf32, SS form, one CTA: the same operand bytes are read as 8 tf32 values per row
+__device__ __forceinline__ void umma_ss_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 template <int CG>
 __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -183,7 +189,8 @@ __global__ void __launch_bounds__((NLDW + 1) * 32, 1) bench_kernel(Params p, lon
                     }
                     const uint32_t acc = (j % 3) != 0;
                     if (elect_one()) {
-                        if (p.ts) umma_ts<CG>(dd[j], a_tm + 8u * (uint32_t)(j & 1), bd[j], p.idesc, acc);
+                        if (p.tf32) umma_ss_tf32(dd[j], ad[j], bd[j], p.idesc, acc);
+                        else if (p.ts) umma_ts<CG>(dd[j], a_tm + 8u * (uint32_t)(j & 1), bd[j], p.idesc, acc);
                         else umma_ss<CG>(dd[j], ad[j], bd[j], p.idesc, acc);
                     }
                     __syncwarp();
@@ -343,6 +350,11 @@ int main(int argc, char **argv) {
     vs.push_back(mk("ss_m128n256_none", 1, 128, 256, "none", "none", 0, NM / 2, 0, 0, 0, 0));
     vs.push_back(mk("ss_m128n256_sw64", 1, 128, 256, "sw64", "sw64", 0, NM / 2, 0, 0, 0, 0));
     vs.push_back(mk("ss_m128n256_sw128", 1, 128, 256, "sw128", "sw128", 0, NM / 2, 0, 0, 0, 0));
+    // --- kind::tf32 (K = 8): the peak of the other instruction kind a float32-exact score could use ---
+    vs.push_back(mk("ss_m128n128_sw32_tf32", 1, 128, 128, "sw32", "sw32", 0, NM, 0, 0, 0, 0));
+    vs.back().p.tf32 = 1; vs.back().p.idesc |= (2u << 7) | (2u << 10);
+    vs.push_back(mk("ss_m128n256_sw32_tf32", 1, 128, 256, "sw32", "sw32", 0, NM / 2, 0, 0, 0, 0));
+    vs.back().p.tf32 = 1; vs.back().p.idesc |= (2u << 7) | (2u << 10);
     // --- A from TMEM ---
     vs.push_back(mk("ts_m128n128_sw32", 1, 128, 128, "sw32", "sw32", 1, NM, 0, 0, 0, 0));
     vs.push_back(mk("ts_m128n128_sw64", 1, 128, 128, "sw32", "sw64", 1, NM, 0, 0, 0, 0));
@@ -434,6 +446,13 @@ int main(int argc, char **argv) {
     if (n_ld)
         printf(", \"cyc_per_ld_iter_avg\": %.1f, \"cyc_per_ld_iter_max\": %.1f, \"ld_warps\": %d, \"bytes_per_iter_per_sm\": %d", ld_sum / n_ld / p.ld_iters,
                ld_max / p.ld_iters, p.ld_warps, 131072 * (p.ld_warps > 8 ? p.ld_warps / 16 : p.ld_warps / 8) + (p.ld_warps == 4 ? 65536 : 0));
+    if (n_mma_blocks && !n_ld) {
+        // whole-chip rate of this instruction stream: flop per MMA (M x N x K x 2) x MMAs x CTAs (or pairs) / kernel time
+        const int M = (int)((p.idesc >> 24) & 0x1f) << 4, N = (int)((p.idesc >> 17) & 0x3f) << 3, K = p.tf32 ? 8 : 16;
+        const double flop = 2.0 * M * N * K * (double)p.n_mma * (grid / sel->cg);
+        printf(", \"M\": %d, \"N\": %d, \"K\": %d, \"kind\": \"%s\", \"tflops_whole_chip\": %.1f", M, N, K, p.tf32 ? "tf32" : "f16",
+               flop / (ms * 1e-3) / 1e12);
+    }
     printf("}\n");
     return 0;
 }

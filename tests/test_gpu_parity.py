@@ -21,11 +21,7 @@ from oracle import fwav_oracle as O
 pytestmark = pytest.mark.gpu
 
 ALL = ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024",
-       "music_k64", "tiny_kfull", "sine_t1100", "music_t3000"]
-if os.environ.get("FWAV_TEST_EXPERIMENTAL") == "1":
-    # tile 2048 -> N=8, ds=2: fixture added after round 1's GPU budget was spent; pinned on the CPU (oracle and the
-    # shared host/device math), joins ALL for good once it has passed on a device
-    ALL = ALL + ["music_t2048"]
+       "music_k64", "tiny_kfull", "sine_t1100", "music_t3000", "music_t2048"]
 SCORE_TOL = 4e-6      # |sgemv - fma chain| on unit-norm heads is ~2e-7; embeddings add 6e-7
 IMPLS = ["ffma", "umma"]
 
@@ -509,13 +505,13 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
 
 
-@pytest.mark.skipif(os.environ.get("FWAV_TEST_EXPERIMENTAL") != "1",
-                    reason="collect_quad_kernel (FWAV_UMMA_QUAD=1) was written after round 1's GPU budget was spent: "
-                           "not yet run on a device; set FWAV_TEST_EXPERIMENTAL=1 to try it")
-@pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None)])
-def test_experimental_four_buffer_collect(ctx, monkeypatch, n_q, top_k, mode):
-    """The four-buffer collect pass must return what the FFMA kernel returns (same table as the odd-shapes test)."""
-    monkeypatch.setenv("FWAV_UMMA_QUAD", "1")
+@pytest.mark.parametrize("layout", ["fat", "quad", "sets"])
+@pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None),
+                                            (20000, 32, "hionly")])
+def test_collect_layouts(ctx, monkeypatch, layout, n_q, top_k, mode):
+    """Every layout of the collect pass (FWAV_UMMA_COLLECT) must return what the FFMA kernel returns, candidates and
+    scores (same kind of table as the odd-shapes test; 20 000 queries: full waves plus a split tail wave)."""
+    monkeypatch.setenv("FWAV_UMMA_COLLECT", layout)
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     ED = 16
@@ -548,7 +544,7 @@ def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
     """Embeddings shaped like range_size 4 (3 live tonal + 4 live transient dimensions, the rest exactly zero):
     the two-MMA compact split must return what the FFMA kernel returns."""
     monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
-    monkeypatch.setenv("FWAV_UMMA_QUAD", quad)
+    monkeypatch.setenv("FWAV_UMMA_COLLECT", "quad" if quad == "1" else "sets")
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     ED = 16
@@ -647,6 +643,225 @@ def test_decode_properties(ctx):
     want = O.decode(idx[:5000], s[:5000], o[:5000], sym[:5000], domains, 5000, N, iterations=6,
                     convergence_eps=0.0, s_damping=0.5)
     assert iters == 6 and np.array_equal(bits(out[:5000 * N]), bits(want))
+
+
+# ------------------------------------------------------------------ round-2 parity gaps ("next round" 1a-1d)
+def _music_table(ctx, seconds, seed, tile=4096, N=16, ds=4, ED=16):
+    from fwav_b200 import _lib, synth
+    sig = synth.music_like(seconds=seconds, rate=44100, seed=seed)
+    n_d = _lib.count_domains(len(sig), tile, ds)
+    d_sig = ctx.upload(sig)
+    d_dom = ctx.alloc(n_d * N * 4)
+    d_emb = ctx.alloc(n_d * ED * 4)
+    ctx.build_domains(d_sig.ptr, len(sig), tile, N, ds, d_dom.ptr)
+    ctx.embed(d_dom.ptr, n_d, N, ED, d_emb.ptr)
+    return n_d, d_emb, d_emb.to_host((n_d, ED), np.float32)
+
+
+@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "fat"), (32, 48, "fat"), (32, None, "sets"), (64, None, "fat"),
+                                              (64, 48, "fat")])
+def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
+    """The fast path works in batches of 2^20 queries (configs 3 and 4 run 2-21 of them per rank).  FWAV_UMMA_BATCH
+    shrinks the batch so that a 5 000-query search crosses batch boundaries seven times: with a pruning mask, a split
+    tail wave in every batch and (cap = 48) forced failures whose batch-local indices go through the second chance
+    and the exact kernels.  Must equal the FFMA kernel bit for bit, and a brute-force float32 search on a sample."""
+    n_d, d_emb, embs = _music_table(ctx, 12.0, 5)
+    assert n_d >= 1 << 16
+    rng = np.random.default_rng(17)
+    n_q = 5000
+    mask = rng.random(n_q) > 0.15
+    mask[768:1024] = False                  # one whole batch-interior CTA group pruned
+    d_act = ctx.upload(mask.astype(np.uint8))
+    out = {}
+    for impl in ("ffma", "umma"):
+        if impl == "umma":
+            monkeypatch.setenv("FWAV_UMMA_BATCH", "768")
+            monkeypatch.setenv("FWAV_UMMA_COLLECT", layout)
+            if cap:
+                monkeypatch.setenv("FWAV_UMMA_CAP", str(cap))
+        set_impl(ctx, impl)
+        d_cand, d_sc = ctx.alloc(n_q * top_k * 4), ctx.alloc(n_q * top_k * 4)
+        before = ctx.search_fallbacks()
+        try:
+            ctx.topk(d_emb.ptr, n_q, d_emb.ptr, n_d, 16, top_k, d_act.ptr, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32),
+                     ctx.search_fallbacks() - before)
+    got, want = out["umma"], out["ffma"]
+    assert np.array_equal(got[0], want[0]), np.flatnonzero((got[0] != want[0]).any(axis=1))[:10]
+    assert np.array_equal(bits(got[1][mask]), bits(want[1][mask]))
+    assert (got[0][~mask] == -1).all()
+    if cap:
+        assert got[2] > 0, "the cap knob should have forced failures in several batches"
+    for i in rng.choice(np.flatnonzero(mask), 24, replace=False):        # oracle: brute force over the whole table
+        sc = embs @ embs[i]
+        kth = np.sort(sc)[-top_k]
+        assert set(np.flatnonzero(sc > kth + SCORE_TOL)) <= set(got[0][i].tolist())
+        assert all(sc[j] >= kth - SCORE_TOL for j in got[0][i])
+    print(f"multi-batch top_k={top_k} cap={cap} {layout}: 7 batches equal to FFMA; {got[2]} queries took a failure route")
+
+
+def _write_wav_stereo24(path, left, right, rate):
+    import wave
+    v = np.stack([left, right], axis=1).astype(np.int32).ravel()
+    payload = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).tobytes()
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(3)
+        w.setframerate(rate)
+        w.writeframes(payload)
+
+
+def test_config4_shape_sample(ctx, tmp_path):
+    """BASELINE.json config 4 at 1/25 length: a 24-bit STEREO file through read_wav_mono (fractal.py:97-112), tile
+    1024 -> range_size 4 (seven live embedding dimensions, crowded scores: the full-split collect pass), domain_step
+    1, top-K 64, 3.46 M domains -- the shape the tensor-core path serves at top_k = 64.  96 sampled ranges against a
+    brute-force float32 search over the whole table + the oracle's affine match, with the north star's tie rules."""
+    import fractal
+    from fwav_b200 import _lib, synth
+    rate, secs, tile, K = 48000, 72.0, 1024, 64
+    left = synth.music_like(secs, rate, seed=4) * 256.0                   # 24-bit scale
+    right = synth.music_like(secs, rate, seed=40) * 256.0 + 1.0           # decorrelated second channel
+    _write_wav_stereo24(tmp_path / "c4.wav", left, right, rate)
+    sig, sr, sw = fractal.read_wav_mono(str(tmp_path / "c4.wav"))
+    assert (sr, sw) == (rate, 3) and len(sig) == len(left)
+    assert np.array_equal(sig, ((left.astype(np.int32) + right.astype(np.int32)) / 2.0).astype(np.float32))
+    N, ds = _lib.geometry(tile)
+    assert (N, ds) == (4, 1)
+    from fwav_b200.prestep import frame_ranges
+    ranges, original_len = frame_ranges(sig, N, 1e-4)
+    set_impl(ctx, "umma")
+    before = ctx.search_fallbacks()
+    try:
+        res = ctx.compress_host(sig, ranges, tile, 16, K, 1e-4, True, 0)
+    finally:
+        set_impl(ctx, "auto")
+    doms = res["domains"]
+    n_d, n_r = len(doms), len(ranges)
+    assert n_d == len(sig) - tile + 1 and n_d >= 1 << 16
+    want_dom = O.build_domains(sig[: tile + 20000], tile, N, ds)
+    assert np.array_equal(bits(doms[:len(want_dom)]), bits(want_dom))
+    embs = O.embed_rows(doms, 16, fast_norm=True).astype(np.float32)
+    assert (np.abs(embs).max(axis=0) > 0).sum() == 7                      # 3 tonal + 4 transient live dimensions
+    rng = np.random.default_rng(11)
+    n_tie = 0
+    for i in np.sort(rng.choice(n_r, 96, replace=False)):
+        if O.is_pruned(ranges[i], 1e-4):
+            assert res["idx"][i] == 0 and np.isinf(res["err"][i])
+            continue
+        sc = embs @ embs[i]
+        order = np.argsort(-sc, kind="stable")[:K + 8]
+        kth, nxt = sc[order[K - 1]], sc[order[K]]
+        w = O.affine_match(ranges[i:i + 1], order[:K][None, :].astype(np.int32), doms, want_all=True)
+        same = res["idx"][i] == w["idx"][0] and res["sym"][i] == w["sym"][0]
+        if not same:
+            e = np.sort(w["all_err"][0])
+            near = abs(e[1] - e[0]) <= 1e-6 * max(abs(e[0]), 1e-30)
+            alias = res["sym"][i] == w["sym"][0] and np.array_equal(doms[res["idx"][i]], doms[w["idx"][0]])
+            assert near or alias or (kth - nxt) <= SCORE_TOL, (i, res["idx"][i], w["idx"][0], kth - nxt)
+            n_tie += 1
+            continue
+        assert abs(res["s"][i] - w["s"][0]) <= 1e-5 * abs(w["s"][0]) + 1e-30
+        assert abs(res["o"][i] - w["o"][0]) <= 1e-5 * abs(w["o"][0]) + 1e-30
+    print(f"config-4 shape ({n_r} ranges x {n_d} domains, K=64, 24-bit stereo): 96 sampled ranges, {n_tie} excused "
+          f"by a tie rule; {ctx.search_fallbacks() - before} queries took a failure route")
+
+
+def test_config1_full_size_end_to_end(ctx):
+    """BASELINE.json config 1 (10 s / 16 kHz sine + noise, tile 1024: 40 000 ranges x 158 977 domains) through the
+    host-buffer C ABI on both search kernels, against the oracle's whole compress() -- every range, not a sample."""
+    from fwav_b200 import synth
+    from fwav_b200.prestep import frame_ranges
+    sig, rate, tile, K = synth.make("c1", 1.0)
+    want = O.compress(sig, tile_size=tile, top_k=K, want_intermediates=True)
+    ranges, original_len = frame_ranges(sig, int(want["range_size"]), 1e-4)
+    assert np.array_equal(bits(ranges), bits(want["ranges"])) and original_len == want["original_len"]
+    assert (len(ranges), len(want["domains"])) == (40000, 158977)
+    g = dict(ranges=want["ranges"], candidates=want["candidates"], domains=want["domains"],
+             embeddings=want["embeddings"], idx=want["idx"], sym=want["sym"], s=want["s"], o=want["o"], err=want["err"])
+    for impl in IMPLS:
+        set_impl(ctx, impl)
+        try:
+            res = ctx.compress_host(sig, ranges, tile, 16, K, 1e-4)
+        finally:
+            set_impl(ctx, "auto")
+        assert np.array_equal(bits(res["domains"]), bits(want["domains"]))
+        st = classify_matches_fast(res, g, K)
+        assert st["boundary"] <= st["ambiguous"], st
+        print("config 1 full size", impl, st)
+        rec, iters, _ = ctx.decode_host(res["domains"], res["idx"], res["s"], res["o"], res["sym"],
+                                        int(want["range_size"]), iterations=8, convergence_eps=0.0, s_damping=0.5)
+        ref = O.decode(res["idx"], res["s"], res["o"], res["sym"], res["domains"], len(ranges), int(want["range_size"]),
+                       iterations=8, convergence_eps=0.0, s_damping=0.5)
+        assert np.array_equal(bits(rec), bits(ref))
+
+
+def classify_matches_fast(res, g, top_k):
+    """classify_matches for tables too large for its per-range brute force over every range: the K boundary gap is
+    only computed for the ranges that differ."""
+    want = O.affine_match(g["ranges"], g["candidates"], g["domains"], want_all=True)
+    diff = np.flatnonzero((res["idx"] != g["idx"]) | (res["sym"] != g["sym"]))
+    embs, doms = g["embeddings"], g["domains"]
+    stats = dict(total=len(g["idx"]), differ=len(diff), near_tie=0, alias=0, boundary=0, ambiguous=0)
+    for i in diff:
+        e = np.sort(want["all_err"][i])
+        if np.isfinite(e[1]) and abs(e[1] - e[0]) <= 1e-6 * max(abs(e[0]), 1e-30):
+            stats["near_tie"] += 1
+            continue
+        if res["sym"][i] == g["sym"][i] and np.array_equal(doms[res["idx"][i]], doms[g["idx"][i]]):
+            stats["alias"] += 1
+            continue
+        sc = embs @ embs[i]
+        top = np.sort(sc)[-(top_k + 1):]
+        assert top[1] - top[0] <= SCORE_TOL, (i, top[1] - top[0])       # only a tied K boundary may change the winner
+        stats["boundary"] += 1
+        stats["ambiguous"] += 1
+    same = np.setdiff1d(np.arange(len(g["idx"])), diff)
+    for k in ("s", "o"):
+        a, b = res[k][same], g[k][same]
+        assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-30), k
+    assert np.array_equal(np.isinf(res["err"]), np.isinf(g["err"]))
+    return stats
+
+
+def test_forged_indices_are_rejected_not_dereferenced(ctx):
+    """A corrupt .fwav (the SHA-256 covers only its own payload) must not make the device read past the domain
+    table: the host entry raises IndexError like the reference's fancy index (fractal.py:1414), the device-pointer
+    decoder reports it after the run without touching foreign memory, and the context stays usable."""
+    import fractal
+    g = golden("sine_t1024")
+    N, n_d = int(g["range_size"]), len(g["domains"])
+    idx = g["idx"].copy()
+    idx[7] = n_d + 5
+    with pytest.raises(IndexError):
+        ctx.decode_host(g["domains"], idx, g["s"], g["o"], g["sym"], N)
+    with pytest.raises(ValueError):
+        ctx.decode_host(g["domains"][:, :3], g["idx"], g["s"], g["o"], g["sym"], N)
+    with pytest.raises(ValueError):
+        ctx.decode_host(g["domains"], g["idx"], g["s"][:-1], g["o"], g["sym"], N)
+    m = list(zip(idx.tolist(), g["s"].tolist(), g["o"].tolist(), g["sym"].tolist(), g["err"].tolist()))
+    with pytest.raises(IndexError):
+        fractal.decompress_audio(m, g["domains"], len(idx), N)
+    # device-pointer form: no host copy of idx to look at, the kernel flags it
+    d_dom, d_idx, d_s, d_o, d_sym = (ctx.upload(a) for a in (g["domains"], idx, g["s"], g["o"], g["sym"]))
+    d_out = ctx.alloc(len(idx) * N * 4)
+    with pytest.raises(IndexError):
+        ctx.decode(d_dom.ptr, n_d, d_idx.ptr, d_s.ptr, d_o.ptr, d_sym.ptr, len(idx), N, 4, 0.0, 16.0, 0.5, d_out.ptr)
+    # caller-supplied candidate table with an entry past the table: treated as padding
+    cand = g["candidates"].copy()
+    cand[3, 5] = n_d + 100
+    want = g["candidates"].copy()
+    want[3, 5] = -1
+    ref = O.affine_match(g["ranges"], want, g["domains"])
+    n_r, K = cand.shape
+    d_r, d_c = ctx.upload(g["ranges"]), ctx.upload(cand)
+    outs = [ctx.alloc(n_r * 4) for _ in range(5)]
+    ctx.affine_match(d_r.ptr, n_r, N, d_dom.ptr, n_d, d_c.ptr, K, 16.0, *[o.ptr for o in outs])
+    assert np.array_equal(outs[0].to_host(n_r, np.int32), ref["idx"])
+    # the context survived all of it
+    out, iters, _ = ctx.decode_host(g["domains"], g["idx"], g["s"], g["o"], g["sym"], N)
+    assert np.array_equal(bits(out[:len(g["dec_default"])]), bits(g["dec_default"]))
 
 
 # ------------------------------------------------------------------ the multi-GPU driver on one GPU
