@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <thread>
+
 #include "common.cuh"
 #include "fwav_math.cuh"
 
@@ -44,6 +46,110 @@ int fwav_ws_reserve(fwav_ctx *ctx, int slot, size_t bytes, void **out) {
     *out = ctx->ws[slot];
     return FWAV_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Page-locked staging ring of the host-buffer entry points (row X1).  A caller's pageable buffer cannot be the
+// end point of an asynchronous copy (the driver stages it and blocks), so such buffers go through a context-owned
+// ring of kRingSlots x kRingSlotBytes of pinned memory, one cudaMemcpyAsync per chunk:
+//   upload   : memcpy(user -> slot) on the calling thread while the DMA of the previous chunks runs;
+//   download : the DMA of chunk k+1.. runs while a helper thread memcpy's chunk k into the user's buffer, and all
+//              of it runs beside the search on the compute stream.
+// Buffers that already are page-locked (fwav_host_alloc, cudaHostRegister, torch pin_memory) take the direct
+// asynchronous copy.
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr size_t kRingSlotBytes = 8u << 20;
+constexpr int kRingSlots = 4;
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int ring_reserve(fwav_ctx *ctx) {
+    if (!ctx->pinned) {
+        cudaError_t e = cudaHostAlloc(&ctx->pinned, kRingSlotBytes * kRingSlots, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->pinned = nullptr;
+            return fwav_set_error(ctx, FWAV_ERR_NOMEM, "cudaHostAlloc of the staging ring: %s", cudaGetErrorString(e));
+        }
+        ctx->pinned_bytes = kRingSlotBytes * kRingSlots;
+        for (int i = 0; i < kRingSlots; ++i) FWAV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+    }
+    return FWAV_OK;
+}
+
+// host -> device on `st`; returns once every byte has left the caller's buffer (the DMA may still be running)
+int upload(fwav_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return FWAV_OK;
+    if (is_pinned(h_src)) {
+        FWAV_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return FWAV_OK;
+    }
+    int rc = ring_reserve(ctx);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int c = 0; off < bytes; ++c, off += kRingSlotBytes) {
+        const int slot = c % kRingSlots;
+        const size_t len = bytes - off < kRingSlotBytes ? bytes - off : kRingSlotBytes;
+        unsigned char *stage = static_cast<unsigned char *>(ctx->pinned) + slot * kRingSlotBytes;
+        if (c >= kRingSlots) FWAV_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));      // the slot's previous DMA has left it
+        memcpy(stage, static_cast<const unsigned char *>(h_src) + off, len);
+        FWAV_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char *>(d_dst) + off, stage, len, cudaMemcpyHostToDevice, st));
+        FWAV_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], st));
+    }
+    return FWAV_OK;
+}
+
+// device -> pageable host through the ring, on the context's copy stream, from a helper thread.  The copy stream
+// already waits for the kernel that produced d_src.
+struct Download {
+    std::thread worker;
+    cudaError_t err = cudaSuccess;
+    bool active = false;
+
+    void start(fwav_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+        active = true;
+        worker = std::thread([=]() {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            cudaStream_t cs = ctx->copy_stream;
+            const size_t n_chunks = (bytes + kRingSlotBytes - 1) / kRingSlotBytes;
+            auto issue = [&](size_t c) {
+                const int slot = (int)(c % kRingSlots);
+                const size_t off = c * kRingSlotBytes, len = bytes - off < kRingSlotBytes ? bytes - off : kRingSlotBytes;
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(static_cast<unsigned char *>(ctx->pinned) + slot * kRingSlotBytes,
+                                        static_cast<const unsigned char *>(d_src) + off, len, cudaMemcpyDeviceToHost, cs);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[slot], cs);
+            };
+            for (size_t c = 0; c < n_chunks && c < (size_t)kRingSlots; ++c) issue(c);
+            for (size_t c = 0; c < n_chunks && e == cudaSuccess; ++c) {
+                const int slot = (int)(c % kRingSlots);
+                const size_t off = c * kRingSlotBytes, len = bytes - off < kRingSlotBytes ? bytes - off : kRingSlotBytes;
+                e = cudaEventSynchronize(ctx->ring_ev[slot]);
+                if (e != cudaSuccess) break;
+                memcpy(static_cast<unsigned char *>(h_dst) + off, static_cast<unsigned char *>(ctx->pinned) + slot * kRingSlotBytes, len);
+                if (c + kRingSlots < n_chunks) issue(c + kRingSlots);
+            }
+            err = e;
+        });
+    }
+    cudaError_t join() {
+        if (active) {
+            worker.join();
+            active = false;
+        }
+        return err;
+    }
+};
+
+}  // namespace
 
 extern "C" {
 
@@ -92,6 +198,8 @@ int fwav_ctx_destroy(fwav_ctx *ctx) {
     if (ctx->d_transient) cudaFree(ctx->d_transient);
     if (ctx->d_w) cudaFree(ctx->d_w);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (cudaEvent_t e : ctx->ring_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -280,23 +388,27 @@ int fwav_compress_device(fwav_ctx *ctx, const float *d_signal, int64_t n_samples
                               d_o, d_sym, d_err, st);
 }
 
-int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, const float *h_ranges,
-                       int64_t n_ranges, int tile_size, int emb_dim, int top_k, double energy_thresh,
-                       int fast_mode, int query_mode, float *h_domains, int32_t *h_idx, float *h_s,
-                       float *h_o, uint8_t *h_sym, float *h_err) {
-    FWAV_ENTER(ctx);
+// Shared body of the two host-buffer compress entry points.  h_ranges_in != NULL: the caller framed the ranges
+// (fwav_compress_host); NULL: the pre-step runs on the device from the raw signal (fwav_compress_signal_host) and
+// h_ranges_out, if given, receives the framed ranges.  *silent (may be NULL) is set when the reference takes its
+// "silent input" early-out (fractal.py:1083): no outputs are written then.
+static int compress_host_impl(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, const float *h_ranges_in,
+                              int64_t n_ranges, int tile_size, int emb_dim, int top_k, double energy_thresh,
+                              int fast_mode, int query_mode, float *h_ranges_out, float *h_domains, int32_t *h_idx,
+                              float *h_s, float *h_o, uint8_t *h_sym, float *h_err, int *silent) {
     cudaStream_t st = ctx->stream;
     int N, ds;
     fwav_geometry(tile_size, &N, &ds);
     const int64_t n_dom = fwav_count_domains(n_samples, tile_size, ds);
     FWAV_REQUIRE(ctx, h_signal && n_dom > 0, "signal of %lld samples is shorter than one tile (%d)",
                  (long long)n_samples, tile_size);
-    FWAV_REQUIRE(ctx, n_ranges == 0 || (h_ranges && h_idx && h_s && h_o && h_sym && h_err), "null buffer");
+    FWAV_REQUIRE(ctx, n_ranges == 0 || (h_idx && h_s && h_o && h_sym && h_err), "null buffer");
+    if (silent) *silent = 0;
     float *d_signal, *d_ranges, *d_domains, *d_emb;
     unsigned char *d_match;
     int rc;
     if ((rc = fwav_ws_reserve(ctx, WS_H_SIGNAL, sizeof(float) * (size_t)n_samples, (void **)&d_signal))) return rc;
-    if ((rc = fwav_ws_reserve(ctx, WS_H_RANGES, sizeof(float) * (size_t)n_ranges * N, (void **)&d_ranges))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_H_RANGES, sizeof(float) * (size_t)n_ranges * N + 8, (void **)&d_ranges))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_H_DOMAINS, sizeof(float) * (size_t)n_dom * N, (void **)&d_domains))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_H_EMB, sizeof(float) * (size_t)n_dom * emb_dim, (void **)&d_emb))) return rc;
     // idx | s | o | err | sym, each 16-byte aligned
@@ -306,28 +418,48 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, 
     float *d_s = (float *)(d_match + stride), *d_o = (float *)(d_match + 2 * stride);
     float *d_err = (float *)(d_match + 3 * stride);
     uint8_t *d_sym = d_match + 4 * stride;
-    FWAV_CUDA(ctx, cudaMemcpyAsync(d_signal, h_signal, sizeof(float) * (size_t)n_samples, cudaMemcpyHostToDevice, st));
-    if (n_ranges)
-        FWAV_CUDA(ctx, cudaMemcpyAsync(d_ranges, h_ranges, sizeof(float) * nr * N, cudaMemcpyHostToDevice, st));
-    // Build the tables first; the domain table (the .fwav payload, the largest transfer of the call) then travels
-    // to the host on the copy stream while the search runs on the compute stream.
+    if (!ctx->copy_stream) FWAV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_event) FWAV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    if ((rc = upload(ctx, d_signal, h_signal, sizeof(float) * (size_t)n_samples, st))) return rc;
+    // The tables are built first; the domain table (the .fwav payload, the largest transfer of the call) then
+    // travels to the host on the copy stream while the pre-step and the search run on the compute stream.
     if ((rc = fwav_launch_domains(ctx, d_signal, n_samples, tile_size, N, ds, d_domains, st))) return rc;
-    if (h_domains) {
-        if (!ctx->copy_stream) FWAV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        if (!ctx->copy_event) FWAV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
-        FWAV_CUDA(ctx, cudaEventRecord(ctx->copy_event, st));
-        FWAV_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
-        FWAV_CUDA(ctx, cudaMemcpyAsync(h_domains, d_domains, sizeof(float) * (size_t)n_dom * N, cudaMemcpyDeviceToHost,
-                                       ctx->copy_stream));
-    }
-    // Once the download has been queued the caller's h_domains is in flight: every exit below goes through
-    // `finish`, which waits for the copy stream before the buffer can be freed or reused.
-    auto finish = [&](int code) -> int {
-        if (h_domains) {
-            const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
-            if (e != cudaSuccess && code == FWAV_OK)
-                code = fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the domain table failed: %s", cudaGetErrorString(e));
+    FWAV_CUDA(ctx, cudaEventRecord(ctx->copy_event, st));
+    if (h_ranges_in) {
+        if ((rc = upload(ctx, d_ranges, h_ranges_in, sizeof(float) * nr * N, st))) return rc;
+    } else {
+        // A0 on the device; the reference's early-out needs the sum of squares on the host: 8 bytes and one sync,
+        // while the domain kernels are already queued behind it
+        double *d_sumsq = reinterpret_cast<double *>(d_ranges + nr * N), h_sumsq = 0.0;
+        if ((rc = fwav_launch_prestep(ctx, d_signal, n_samples, N, energy_thresh, d_ranges, d_sumsq, st))) return rc;
+        FWAV_CUDA(ctx, cudaMemcpyAsync(&h_sumsq, d_sumsq, sizeof(double), cudaMemcpyDeviceToHost, st));
+        FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+        if ((float)h_sumsq < 1e-8f) {            // np.sum(weighted_signal ** 2) < 1e-8 (:1083); float64 sum here
+            if (silent) *silent = 1;
+            return FWAV_OK;
         }
+    }
+    // Once a download has been queued the caller's buffers are in flight: every exit below goes through `finish`,
+    // which waits for the copy stream (and the helper thread) before they can be freed or reused.
+    Download dl;
+    bool direct_dl = false;
+    if (h_domains) {
+        FWAV_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+        const size_t bytes = sizeof(float) * (size_t)n_dom * N;
+        if (is_pinned(h_domains)) {
+            direct_dl = true;
+            FWAV_CUDA(ctx, cudaMemcpyAsync(h_domains, d_domains, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        } else {
+            if ((rc = ring_reserve(ctx))) return rc;
+            FWAV_CUDA(ctx, cudaStreamSynchronize(st));      // the upload may still own ring slots
+            dl.start(ctx, h_domains, d_domains, bytes);
+        }
+    }
+    auto finish = [&](int code) -> int {
+        cudaError_t e = dl.join();
+        if (e == cudaSuccess && direct_dl) e = cudaStreamSynchronize(ctx->copy_stream);
+        if (e != cudaSuccess && code == FWAV_OK)
+            code = fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the domain table failed: %s", cudaGetErrorString(e));
         return code;
     };
     if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return finish(rc);
@@ -337,15 +469,46 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, 
     if (rc) return finish(rc);
     cudaError_t ce = cudaSuccess;
     if (n_ranges) {
-        const struct { void *h; const void *d; size_t n; } out[5] = {
-            {h_idx, d_idx, nr * 4}, {h_s, d_s, nr * 4}, {h_o, d_o, nr * 4}, {h_err, d_err, nr * 4}, {h_sym, d_sym, nr}};
+        const struct { void *h; const void *d; size_t n; } out[6] = {
+            {h_idx, d_idx, nr * 4}, {h_s, d_s, nr * 4}, {h_o, d_o, nr * 4}, {h_err, d_err, nr * 4}, {h_sym, d_sym, nr},
+            {h_ranges_out, d_ranges, h_ranges_out ? nr * N * 4 : 0}};
         for (const auto &o : out)
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(o.h, o.d, o.n, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess && o.n) ce = cudaMemcpyAsync(o.h, o.d, o.n, cudaMemcpyDeviceToHost, st);
     }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess)
         return finish(fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the matches failed: %s", cudaGetErrorString(ce)));
     return finish(FWAV_OK);
+}
+
+int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, const float *h_ranges,
+                       int64_t n_ranges, int tile_size, int emb_dim, int top_k, double energy_thresh,
+                       int fast_mode, int query_mode, float *h_domains, int32_t *h_idx, float *h_s,
+                       float *h_o, uint8_t *h_sym, float *h_err) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, n_ranges == 0 || h_ranges, "null buffer");
+    return compress_host_impl(ctx, h_signal, n_samples, h_ranges, n_ranges, tile_size, emb_dim, top_k, energy_thresh,
+                              fast_mode, query_mode, nullptr, h_domains, h_idx, h_s, h_o, h_sym, h_err, nullptr);
+}
+
+int fwav_compress_signal_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples, int tile_size, int emb_dim,
+                              int top_k, double energy_thresh, int fast_mode, int query_mode, float *h_ranges,
+                              float *h_domains, int32_t *h_idx, float *h_s, float *h_o, uint8_t *h_sym,
+                              float *h_err, int *silent) {
+    FWAV_ENTER(ctx);
+    int N, ds;
+    fwav_geometry(tile_size, &N, &ds);
+    const int64_t n_ranges = (n_samples + N - 1) / N;
+    return compress_host_impl(ctx, h_signal, n_samples, nullptr, n_ranges, tile_size, emb_dim, top_k, energy_thresh,
+                              fast_mode, query_mode, h_ranges, h_domains, h_idx, h_s, h_o, h_sym, h_err, silent);
+}
+
+int fwav_prepare_ranges(fwav_ctx *ctx, const float *d_signal, int64_t n_samples, int range_size,
+                        double energy_thresh, float *d_ranges, double *d_sumsq, void *stream) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, d_signal && d_ranges && d_sumsq, "null buffer");
+    return fwav_launch_prestep(ctx, d_signal, n_samples, range_size, energy_thresh, d_ranges, d_sumsq,
+                               fwav_stream(ctx, stream));
 }
 
 int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains, const int32_t *h_idx,

@@ -35,10 +35,11 @@ struct fwav_ctx {
     double *d_tonal = nullptr, *d_transient = nullptr, *d_w = nullptr;
 
     // grow-only scratch arenas (device) and a pinned host staging block
-    void *ws[24] = {nullptr};
-    size_t ws_bytes[24] = {0};
-    void *pinned = nullptr;
+    void *ws[32] = {nullptr};
+    size_t ws_bytes[32] = {0};
+    void *pinned = nullptr;               // staging ring of the host-buffer entry points (api.cu)
     size_t pinned_bytes = 0;
+    cudaEvent_t ring_ev[4] = {};
 };
 
 // scratch slots
@@ -47,9 +48,10 @@ enum {
     WS_UMMA_THETA, WS_UMMA_CBUF, WS_UMMA_CNT, WS_UMMA_FAIL, WS_UMMA_FB, WS_UMMA_PARTS, WS_FFMA_PARTS, WS_UMMA_TAIL,
     // device mirrors of the host-buffer entry points
     WS_H_SIGNAL, WS_H_RANGES, WS_H_DOMAINS, WS_H_EMB, WS_H_MATCH, WS_H_OUT,
+    WS_PRESTEP, WS_DECODE_TILES,
     WS_COUNT
 };
-static_assert(WS_COUNT <= 24, "grow fwav_ctx::ws");
+static_assert(WS_COUNT <= 32, "grow fwav_ctx::ws");
 
 int fwav_set_error(fwav_ctx *ctx, int code, const char *fmt, ...);
 int fwav_ws_reserve(fwav_ctx *ctx, int slot, size_t bytes, void **out);
@@ -81,6 +83,8 @@ static inline cudaStream_t fwav_stream(fwav_ctx *ctx, void *stream) {
 // internal launchers (one per .cu file)
 int fwav_launch_domains(fwav_ctx *ctx, const float *d_signal, int64_t n, int tile, int N, int ds,
                         float *d_domains, cudaStream_t st);
+int fwav_launch_prestep(fwav_ctx *ctx, const float *d_signal, int64_t n, int N, double energy_thresh, float *d_ranges,
+                        double *d_sumsq, cudaStream_t st);
 int fwav_launch_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int N, int emb_dim,
                       float *d_emb, cudaStream_t st);
 int fwav_launch_activity(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N, double thr,

@@ -18,6 +18,50 @@ namespace fwm {
 constexpr int kMaxRangeSize = 255;
 
 // ---------------------------------------------------------------------------
+// A0  pre-step of compress_audio: voiced gate, masking, reflect padding, framing (fractal.py:880-909, 1074-1112).
+// ---------------------------------------------------------------------------
+// np.pad(x, (0, pad), mode='reflect') with pad < n: position i of the padded array reads x[reflect_index(i, n)]
+FWAV_HD long long reflect_index(long long i, long long n) { return i < n ? i : 2 * (n - 1) - i; }
+
+// energy of frame f: np.mean(frames * frames, axis=1) in float32, numpy's pairwise order over the frame (:890-892)
+template <int NS = 0, class Sig>
+FWAV_HD float frame_energy(Sig sig, long long f, int frame_size, long long n) {
+    const long long start = f * frame_size;
+    auto sq = [&](int k) { const float v = sig(reflect_index(start + k, n)); return npm::mul(v, v); };
+    return npm::mean_n<NS>(sq, frame_size);
+}
+
+// np.convolve(energies, ones(5, float32) / 5, mode='same') at frame f, n_frames >= 5 (:894-896).  Interior outputs
+// are numpy's small-kernel loop: a float32 multiply-add chain over ascending taps, each step rounded.  The two
+// outputs at either end have fewer taps and go through the dot-product routine (OpenBLAS sdot): float32 products
+// accumulated in float64, rounded once.  Both forms verified against numpy 2.3 / OpenBLAS 0.3.30.
+template <class E>
+FWAV_HD float smooth5(E e, long long f, long long n_frames) {
+    const float w = npm::div(1.0f, 5.0f);
+    const long long lo = f - 2 < 0 ? 0 : f - 2, hi = f + 3 > n_frames ? n_frames : f + 3;
+    if (hi - lo == 5) {
+        float acc = 0.0f;
+        for (long long j = lo; j < hi; ++j) acc = npm::add(acc, npm::mul(e(j), w));
+        return acc;
+    }
+    double d = 0.0;
+    for (long long j = lo; j < hi; ++j) d += (double)npm::mul(e(j), w);
+    return (float)d;
+}
+
+// hysteresis of :901-907 as a scan: a frame whose smoothed energy exceeds the threshold switches the gate on, one
+// below the low threshold switches it off, any other keeps the previous state.  Encoded so that the running
+// MAXIMUM of the keys carries the latest switch: key = 2 * f + on for a switching frame, -1 otherwise; the gate at
+// frame f is (max key up to f) & 1, off while that maximum is still -1.  Thresholds are Python floats cast to
+// float32 at the comparison (NEP 50).
+FWAV_HD long long gate_key(float smoothed, long long f, double energy_threshold) {
+    const float hi = (float)energy_threshold, lo = (float)(energy_threshold * 0.5);
+    if (smoothed > hi) return 2 * f + 1;
+    if (smoothed < lo) return 2 * f;
+    return -1;
+}
+
+// ---------------------------------------------------------------------------
 // A1  domain value (fractal.py:314-327): mean of `run` consecutive samples.
 // run = tile_size // range_size is < 512 for every legal tile_size.
 // ---------------------------------------------------------------------------

@@ -1007,19 +1007,9 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 // that fail (too few candidates, buffer overflow, boundary within the slack) go
 // on the list for the exact MODE_LISTS kernel.
 // ---------------------------------------------------------------------------
-// ---------------------------------------------------------------------------
-// EXPERIMENTAL (FWAV_UMMA_QUAD=1; written at the end of round 1, NOT yet run on a GPU -- the default path never
-// reaches it): the collect pass with FOUR 128-column accumulator buffers, two per epilogue set.
-// DESIGN.md section 7 has the arithmetic: with two 256-column buffers a set of epilogue warps idles while its only
-// buffer goes through the MMA hand-over; here a stage is one 128-domain tile (M128 N128 K16 MMAs), set s takes
-// the tiles t = s (mod 2) and alternates between buffers s and s + 2, a warp takes 64 columns of an own tile
-// (one pair of loads) and hands the buffer back right after the loads.  Same inputs, outputs and candidate-buffer
-// layout as scan_kernel<MODE_COLLECT, HI, 1> (group = set + 2 * column half), so finalize_kernel does not care.
-// ---------------------------------------------------------------------------
 constexpr int kQuadRing = 16;                                  // 128-domain tiles in flight (8 KB each: hi | lo)
 constexpr uint32_t kQuadOffBars = kTileBytes;                  // after the query tile
 constexpr uint32_t kQuadOffRing = kTileBytes + 1024;           // 1024-aligned
-constexpr uint32_t kQuadSmem = kQuadOffRing + kQuadRing * kTileBytes;
 constexpr uint32_t kQuadIdesc = (1u << 4) | ((uint32_t)(kDTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);   // D=F32, A=B=F16, N=128, M=128
 
 __device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
@@ -1031,14 +1021,52 @@ __device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_de
         : "memory");
 }
 
-template <bool HI, bool COMPACT = false>
-__global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kernel(const ScanArgs a) {
-    constexpr int kEpi = 16, kThreads = n_threads(MODE_COLLECT);
-    constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;
+// ---------------------------------------------------------------------------
+// collect4_kernel: the hi*hi-only collect pass with FOUR 128-column accumulator buffers (round 2).
+//
+// What bounded scan_kernel<MODE_COLLECT, true, 1>: TMEM has room for two 256-column accumulators
+// only, a buffer is held for two rounds of load + reduce before it goes back, and ONE issue of a tcgen05.mma is a
+// serial chain (two mbarrier waits, the instruction -- which blocks its thread until the tensor pipe takes it --
+// two commits) several hundred cycles long.  Here a tile is 128 domains (M128 N128 K16), TMEM holds four
+// accumulators, up to four threads issue (ISS), a set of epilogue warps owns the tiles t = s (mod 2) and finds its
+// next accumulator ready when it comes back.  Two epilogue layouts:
+//   EPI = 16 ("thin"): warp = (TMEM lane quadrant, set, column half); one tcgen05.ld x64 per own tile, the buffer
+//                      goes back right after it, 96 registers, four warps per scheduler;
+//   EPI = 8  ("fat"):  warp = (lane quadrant, set) reads all 128 columns of an own tile; the loads are software-
+//                      pipelined across tiles (columns 0-63 of the next own tile travel while columns 64-127 of this
+//                      one are reduced), 128 data registers, two warps per scheduler.
+// Hits (a score >= the row's threshold) are staged eight at a time in shared memory and leave as whole 32-byte
+// sectors, so L2 never has to fetch a sector from DRAM to merge a 4-byte store into it (round 1: 6.1 GB of such
+// reads per launch).  The rare path is compact on purpose (which columns pass goes into a bit mask first, the store
+// sequence exists once per pair of chunks): the loop body stays within the instruction cache.
+// Candidate lists: EPI = 16 -> part (set + 2 * column half) of the row's buffer, as scan_kernel; EPI = 8 -> parts
+// (2 * set, 2 * set + 1) laid end to end.  finalize_kernel reads the parts as before.
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int c4_threads(int epi, int iss) { return (epi + 1 + iss) * 32; }
+__host__ __device__ constexpr int c4_regs(int epi, int iss) { return epi == 16 ? 96 : (iss == 4 ? 152 : 168); }
+constexpr uint32_t kC4OffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
+__host__ __device__ constexpr uint32_t c4_smem(int epi) { return kC4OffStage + (uint32_t)epi * 8 * 32 * 4; }
+
+// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : FWAV_R32(v), FWAV_R32(w)
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int EPI, int ISS>
+__global__ void __maxnreg__(c4_regs(EPI, ISS)) collect4_kernel(const ScanArgs a) {
+    constexpr int kThreads = c4_threads(EPI, ISS);
+    constexpr uint32_t kOpBytes = kPartBytes;                    // the hi parts alone
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_q = a.n_q;
-    const int dbg = a.dbg;
     const uint8_t *__restrict__ active = a.active;
     const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
     const long long q_base = (long long)group_id * kQTile;
@@ -1064,11 +1092,11 @@ __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kerne
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kQuadRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kEpi / 2); }
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, EPI / 2); }
         mbar_init(bar_a, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kEpi) {
+    if (warp == EPI) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -1081,8 +1109,8 @@ __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kerne
     const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;
     const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
 
-    if (warp == kEpi) {
-        // ===== producer: one bulk copy per tile ([hi | lo] is contiguous in the packed table) =====
+    if (warp == EPI) {
+        // ===== producer: one bulk copy per tile (the hi part is the first 4 KB of a packed tile) =====
         if (lane == 0) {
             mbar_expect_tx(bar_a, kOpBytes);
             bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kOpBytes, bar_a);
@@ -1096,217 +1124,33 @@ __global__ void __launch_bounds__(n_threads(MODE_COLLECT), 1) collect_quad_kerne
                 if (++tt == t_hi) tt = t_lo;
             }
         }
-    } else if (warp > kEpi) {
-        // ===== two MMA issuers: thread i owns the tiles t = i (mod 2), i.e. buffers i and i + 2 =====
+    } else if (warp > EPI) {
+        // ===== MMA issuers: thread i owns the tiles t = i (mod ISS); tile t goes into buffer t & 3 =====
         if (lane == 0) {
             mbar_wait(bar_a, 0);
-            const uint32_t a_hi = smem_u32(smem + kOffA);
-            const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_hi + kPartBytes);
-            for (int t = warp - (kEpi + 1); t < n_visit; t += 2) {
+            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
+            for (int t = warp - (EPI + 1); t < n_visit; t += ISS) {
                 const int s = t & (kQuadRing - 1), buf = t & 3;
-                const uint32_t b_hi = smem_u32(smem + kQuadOffRing + s * kTileBytes);
-                const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_hi + kPartBytes);
-                const uint32_t d = tmem_base + (uint32_t)(buf * kDTile);
+                const uint64_t db_hi = smem_desc(smem_u32(smem + kQuadOffRing + s * kTileBytes));
                 mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQuadRing) & 1));
                 mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((t >> 2) & 1) ^ 1));
                 tc_fence_after();
-                if (HI) {
-                    umma_f16_m128n128(d, da_hi, db_hi, 0);
-                } else if (COMPACT) {
-                    umma_f16_m128n128(d, da_lo, db_lo, 0);
-                    umma_f16_m128n128(d, da_hi, db_hi, 1);
-                } else {
-                    umma_f16_m128n128(d, da_hi, db_lo, 0);
-                    umma_f16_m128n128(d, da_lo, db_hi, 1);
-                    umma_f16_m128n128(d, da_hi, db_hi, 1);
-                }
+                umma_f16_m128n128(tmem_base + (uint32_t)(buf * kDTile), da_hi, db_hi, 0);
                 umma_commit<1>(bar_tfull + 8 * buf);
                 umma_commit<1>(bar_empty + 8 * s);
             }
         }
     } else {
-        // ===== epilogue: one query row per thread; warp = (lane quadrant, set, column half of the tile) =====
-        const int quad = warp & 3, grp = warp >> 2, set = grp & 1, colhalf = grp >> 1;
-        const long long q = q_base + quad * 32 + lane;
-        const float tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
-        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + grp) * (long long)a.cap;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(colhalf * 64);
-        int cnt = 0;
-        int tt = t_first + set;
-        if (tt >= t_hi) tt -= n_visit;
-        for (int t = set; t < n_visit; t += 2) {
-            const int buf = t & 3;
-            mbar_wait_hot(bar_tfull + 8 * buf, (uint32_t)((t >> 2) & 1));
-            tc_fence_after();
-            uint32_t x0[32], x1[32];
-            tmem_ld32(t_lane + (uint32_t)(buf * kDTile), x0);
-            tmem_ld32(t_lane + (uint32_t)(buf * kDTile) + 32, x1);
-            tmem_wait_ld2(x0, x1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
-            const float ma = chunk_max(x0);
-            const int col0 = tt * kDTile + colhalf * 64;
-            tt += 2;
-            if (tt >= t_hi) tt -= n_visit;
-            const float mb = chunk_max(x1);
-            if (ma >= tau)
-                for_each_ge(x0, tau, [&](int j) {
-                    if (cnt < a.cap) cbuf[cnt] = col0 + j;
-                    ++cnt;
-                });
-            if (mb >= tau)
-                for_each_ge(x1, tau, [&](int j) {
-                    if (cnt < a.cap) cbuf[cnt] = col0 + 32 + j;
-                    ++cnt;
-                });
-        }
-        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + grp] = cnt;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kEpi) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------
-// collect_fat_kernel: the hi*hi-only collect pass with FOUR 128-column accumulator buffers and EIGHT "fat"
-// epilogue warps (two per scheduler), the round-2 layout of the dominant kernel.
-//
-// What bounded scan_kernel<MODE_COLLECT, true, 1>: (a) ~40 instructions of waiting, addressing and
-// loop control per warp and stage against 36-72 max instructions, on the same ALU pipe; (b) with 96 registers a
-// warp holds two 32-column chunks, so a 256-column buffer is held for two rounds of load + reduce before it goes
-// back to the MMA thread, and TMEM has room for two such buffers only (Little's law on 512 columns).  Here
-//   * a tile is 128 domains (M128 N128 K16: 136 cycles, 272 per 256 columns -- below the ALU floor of the
-//     reduction), so TMEM holds four accumulators and a set of warps always finds its next one ready;
-//   * warp = (TMEM lane quadrant, set); set s owns the tiles t = s (mod 2), i.e. buffers s and s + 2, and a warp
-//     reads ALL 128 columns of an own tile with two tcgen05.ld x64 (128 data registers, 352 threads per CTA);
-//     the buffer goes back as soon as the second load has landed: before anything is reduced;
-//   * the loads are software-pipelined across tiles: columns 0-63 of the next own tile travel while columns
-//     64-127 of this one are reduced, columns 64-127 while its columns 0-63 are;
-//   * per warp and tile: two mbarrier operations, two loads, 2 x 33 max/compare instructions.
-// Hits (a score >= the row's threshold) are staged eight at a time in shared memory and leave as whole 32-byte
-// sectors, so L2 never has to fetch a sector from DRAM to merge a 4-byte store into it (round 1: 6.1 GB of such
-// reads per launch).  A thread's list is the two parts (2 * set, 2 * set + 1) of the row's candidate buffer, laid
-// end to end; finalize_kernel reads the parts as before.
-// ---------------------------------------------------------------------------
-constexpr int kFatEpi = 8;
-constexpr int kFatThreads = (kFatEpi + 3) * 32;
-constexpr uint32_t kFatOffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
-constexpr uint32_t kFatSmem = kFatOffStage + kFatEpi * 8 * 32 * 4;
-
-// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : FWAV_R32(v), FWAV_R32(w)
-        : "r"(taddr)
-        : "memory");
-}
-
-template <bool HI>
-__global__ void __launch_bounds__(kFatThreads, 1) collect_fat_kernel(const ScanArgs a) {
-    constexpr uint32_t kOpBytes = HI ? kPartBytes : kTileBytes;
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_q = a.n_q;
-    const uint8_t *__restrict__ active = a.active;
-    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
-    const long long q_base = (long long)group_id * kQTile;
-    const uint32_t bars = smem_u32(smem + kQuadOffBars);
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQuadRing, bar_tfull = bars + 16 * kQuadRing,
-                   bar_tempty = bar_tfull + 32, bar_a = bar_tempty + 32;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQuadOffBars + 16 * kQuadRing + 80);
-
-    {   // energy-pruned stretch: nothing to scan
-        int any = 0;
-        for (int i = threadIdx.x; i < kQTile; i += kFatThreads) {
-            const long long q = q_base + i;
-            if (q < n_q && (!active || active[q])) any = 1;
-        }
-        if (!__syncthreads_or(any)) {
-            for (int i = threadIdx.x; i < kQTile; i += kFatThreads) {
-                const long long q = q_base + i;
-                if (q < n_q)
-                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
-            }
-            return;
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kQuadRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kFatEpi / 2); }
-        mbar_init(bar_a, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kFatEpi) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // this CTA's share of the table, in 128-domain tiles; the scan starts at the CTA's own rows and wraps around
-    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
-    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;
-    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
-
-    if (warp == kFatEpi) {
-        // ===== producer: one bulk copy per tile ([hi | lo] is contiguous in the packed table) =====
-        if (lane == 0) {
-            mbar_expect_tx(bar_a, kOpBytes);
-            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kOpBytes, bar_a);
-            int tt = t_first;
-            for (int t = 0; t < n_visit; ++t) {
-                const int s = t & (kQuadRing - 1);
-                mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / kQuadRing) & 1) ^ 1));
-                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
-                bulk_g2s(smem_u32(smem + kQuadOffRing + s * kTileBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kOpBytes,
-                         bar_full + 8 * s);
-                if (++tt == t_hi) tt = t_lo;
-            }
-        }
-    } else if (warp > kFatEpi) {
-        // ===== two MMA issuers: thread i owns the tiles t = i (mod 2), i.e. buffers i and i + 2 =====
-        if (lane == 0) {
-            mbar_wait(bar_a, 0);
-            const uint32_t a_hi = smem_u32(smem + kOffA);
-            const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_hi + kPartBytes);
-            for (int t = warp - (kFatEpi + 1); t < n_visit; t += 2) {
-                const int s = t & (kQuadRing - 1), buf = t & 3;
-                const uint32_t b_hi = smem_u32(smem + kQuadOffRing + s * kTileBytes);
-                const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_hi + kPartBytes);
-                const uint32_t d = tmem_base + (uint32_t)(buf * kDTile);
-                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQuadRing) & 1));
-                mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((t >> 2) & 1) ^ 1));
-                tc_fence_after();
-                if (HI) {
-                    umma_f16_m128n128(d, da_hi, db_hi, 0);
-                } else {
-                    umma_f16_m128n128(d, da_hi, db_lo, 0);
-                    umma_f16_m128n128(d, da_lo, db_hi, 1);
-                    umma_f16_m128n128(d, da_hi, db_hi, 1);
-                }
-                umma_commit<1>(bar_tfull + 8 * buf);
-                umma_commit<1>(bar_empty + 8 * s);
-            }
-        }
-    } else {
-        // ===== epilogue: one query row per thread; warp = (lane quadrant, set) =====
-        const int quad = warp & 3, set = warp >> 2;
+        // ===== epilogue: one query row per thread =====
+        const int quad = warp & 3, set = (warp >> 2) & 1, colhalf = warp >> 3;      // colhalf: EPI == 16 only
         const long long q = q_base + quad * 32 + lane;
         const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
-        const int cap2 = 2 * a.cap;                             // this thread's list: parts 2 * set and 2 * set + 1
-        int32_t *list = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + 2 * set) * (long long)a.cap;
-        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kFatOffStage) + warp * 256 + lane;    // slot k: stg[32 * k]
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // this thread's list: EPI == 16: part set + 2 * colhalf; EPI == 8: parts 2 * set and 2 * set + 1, end to end
+        const int part0 = EPI == 16 ? set + 2 * colhalf : 2 * set;
+        const int room = EPI == 16 ? a.cap : 2 * a.cap;
+        int32_t *list = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + part0) * (long long)a.cap;
+        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kC4OffStage) + warp * 256 + lane;    // slot k: stg[32 * k]
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(EPI == 16 ? colhalf * 64 : 0);
         int cnt = 0;
         // eight staged indices -> one 32-byte sector of the list
         auto flush = [&](int at) {
@@ -1316,28 +1160,43 @@ __global__ void __launch_bounds__(kFatThreads, 1) collect_fat_kernel(const ScanA
             dst[0] = lo4;
             dst[1] = hi4;
         };
-        auto push = [&](int id) {
-            stg[(cnt & 7) * 32] = (uint32_t)id;
-            if ((cnt & 7) == 7 && cnt < cap2) flush(cnt - 7);
-            ++cnt;
-        };
-        // rare path (0.4 % of a thread's chunks): which columns pass goes into a bit mask first, so that the store
-        // sequence exists once per chunk and the loop body stays within the instruction cache
-        auto look = [&](const uint32_t (&x)[32], int col) {
-            if (chunk_max(x) >= tau) {
-                unsigned mask = 0u;
-                for_each_ge(x, tau, [&](int j) { mask |= 1u << j; });
+        // one pair of 32-column chunks: both maxima first (two independent trees), one compare for the pair
+        auto look2 = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32], int col) {
+            const float m0 = chunk_max(x0), m1 = chunk_max(x1);
+            if (fmaxf(m0, m1) >= tau) {
+                unsigned long long mask = 0ull;
+                if (m0 >= tau) for_each_ge(x0, tau, [&](int j) { mask |= 1ull << j; });
+                if (m1 >= tau) for_each_ge(x1, tau, [&](int j) { mask |= 1ull << (32 + j); });
                 while (mask) {
-                    push(col + __ffs(mask) - 1);
+                    stg[(cnt & 7) * 32] = (uint32_t)(col + __ffsll((long long)mask) - 1);
+                    if ((cnt & 7) == 7 && cnt < room) flush(cnt - 7);
+                    ++cnt;
                     mask &= mask - 1;
                 }
             }
         };
         const int n_own = (n_visit - set + 1) / 2;               // tiles set, set + 2, ... below n_visit
-        if (n_own > 0) {
+        int tt = t_first + set;
+        if (tt >= t_hi) tt -= n_visit;
+        if (EPI == 16) {
+            for (int i = 0; i < n_own; ++i) {
+                const int buf = set + 2 * (i & 1);
+                uint32_t x0[32], x1[32];
+                mbar_wait(bar_tfull + 8 * buf, (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                tmem_ld64(t_lane + (uint32_t)(buf * kDTile), x0, x1);
+                tmem_wait_ld2(x0, x1);
+                // this warp's share of the accumulator is in registers: hand it back before looking at it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
+                const int col = tt * kDTile + colhalf * 64;
+                tt += 2;
+                if (tt >= t_hi) tt -= n_visit;
+                look2(x0, x1, col);
+            }
+        } else if (n_own > 0) {
             uint32_t p0[32], p1[32], r0[32], r1[32];             // columns 0-63 and 64-127 of the tile in hand
-            int tt = t_first + set;
-            if (tt >= t_hi) tt -= n_visit;
             mbar_wait(bar_tfull + 8 * set, 0);
             tc_fence_after();
             tmem_ld64(t_lane + (uint32_t)(set * kDTile), p0, p1);
@@ -1348,8 +1207,7 @@ __global__ void __launch_bounds__(kFatThreads, 1) collect_fat_kernel(const ScanA
                 const int col = tt * kDTile;
                 tt += 2;
                 if (tt >= t_hi) tt -= n_visit;
-                look(p0, col);
-                look(p1, col + 32);
+                look2(p0, p1, col);
                 tmem_wait_ld2(r0, r1);
                 // the whole tile is in registers: hand the accumulator back
                 tc_fence_before();
@@ -1362,25 +1220,28 @@ __global__ void __launch_bounds__(kFatThreads, 1) collect_fat_kernel(const ScanA
                     tc_fence_after();
                     tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile), p0, p1);
                 }
-                look(r0, col + 64);
-                look(r1, col + 96);
+                look2(r0, r1, col + 64);
                 if (more) {
                     tmem_wait_ld2(p0, p1);
                     tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile) + 64, r0, r1);
                 }
             }
         }
-        if ((cnt & 7) && cnt < cap2) flush(cnt & ~7);            // the last, partial sector (the count says how much of it is valid)
+        if ((cnt & 7) && cnt < room) flush(cnt & ~7);            // the last, partial sector (the count says how much of it is valid)
         if (q < n_q) {
-            const int c0 = cnt < a.cap ? cnt : a.cap;
-            int *cc = a.ccount + (q * a.n_split + split) * 4 + 2 * set;
-            cc[0] = c0;
-            cc[1] = cnt - c0;                                    // above cap: finalize_kernel reads it as an overflow
+            int *cc = a.ccount + (q * a.n_split + split) * 4 + part0;
+            if (EPI == 16) {
+                cc[0] = cnt;                                     // above cap: finalize_kernel reads it as an overflow
+            } else {
+                const int c0 = cnt < a.cap ? cnt : a.cap;
+                cc[0] = c0;
+                cc[1] = cnt - c0;
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kFatEpi) {
+    if (warp == EPI) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -1646,7 +1507,7 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
-constexpr bool kDefaultFat = false;           // default layout of the hi*hi-only collect pass (see FWAV_UMMA_COLLECT)
+constexpr const char *kDefaultCollect = "sets"; // default layout of the hi*hi-only collect pass (see FWAV_UMMA_COLLECT)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
 inline int grid_for(const fwav_ctx *ctx, long long work) {
@@ -1665,20 +1526,11 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
     return FWAV_OK;
 }
 
-// the experimental four-buffer collect pass (FWAV_UMMA_QUAD=1): one CTA per 128 queries and table share
-template <bool HI, bool COMPACT = false>
-int launch_quad(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_quad_kernel<HI, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQuadSmem));
-    collect_quad_kernel<HI, COMPACT><<<(unsigned)(groups * split), n_threads(MODE_COLLECT), kQuadSmem, st>>>(a);
-    FWAV_LAUNCH_CHECK(ctx);
-    return FWAV_OK;
-}
-
-// the fat-warp four-buffer collect pass (hi*hi-only; see collect_fat_kernel): one CTA per 128 queries and table share
-template <bool HI>
-int launch_fat(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_fat_kernel<HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFatSmem));
-    collect_fat_kernel<HI><<<(unsigned)(groups * split), kFatThreads, kFatSmem, st>>>(a);
+// the four-buffer collect pass (hi*hi-only batches; see collect4_kernel): one CTA per 128 queries and table share
+template <int EPI, int ISS>
+int launch_c4(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect4_kernel<EPI, ISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c4_smem(EPI)));
+    collect4_kernel<EPI, ISS><<<(unsigned)(groups * split), c4_threads(EPI, ISS), c4_smem(EPI), st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1823,11 +1675,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = pack(d_emb, n_d, s_stages * 2, d_es, sample_stride, 1))) return rc;
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
-    // layout of the hi*hi-only collect pass: "fat" (collect_fat_kernel), "sets" (scan_kernel, two epilogue sets),
-    // "quad" (collect_quad_kernel); every layout returns the same candidates
+    // layout of the hi*hi-only collect pass: "sets" (scan_kernel: two 256-column buffers, two epilogue sets) or
+    // collect4_kernel as "thin4" / "thin2" / "fat4" / "fat2" (epilogue layout, issuer threads); all return the same
     const char *layout_env = getenv("FWAV_UMMA_COLLECT");
-    const bool quad = single && layout_env && !strcmp(layout_env, "quad");
-    const bool fat = single && !quad && (layout_env ? !strcmp(layout_env, "fat") : kDefaultFat);
+    const char *layout = single ? (layout_env ? layout_env : kDefaultCollect) : "sets";
     long long batch_cap = kBatchQueries;
     if (const char *batch_env = getenv("FWAV_UMMA_BATCH")) {  // test knob: small batches exercise the multi-batch loop
         const long long v = atoll(batch_env);
@@ -1937,11 +1788,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
-            if (fat && hi_only)
-                rc = launch_fat<true>(ctx, ax, g, sp, st);
-            else if (quad)
-                rc = hi_only ? launch_quad<true>(ctx, ax, g, sp, st)
-                   : compact ? launch_quad<false, true>(ctx, ax, g, sp, st) : launch_quad<false>(ctx, ax, g, sp, st);
+            if (hi_only && !strcmp(layout, "thin4")) rc = launch_c4<16, 4>(ctx, ax, g, sp, st);
+            else if (hi_only && !strcmp(layout, "thin2")) rc = launch_c4<16, 2>(ctx, ax, g, sp, st);
+            else if (hi_only && !strcmp(layout, "fat4")) rc = launch_c4<8, 4>(ctx, ax, g, sp, st);
+            else if (hi_only && !strcmp(layout, "fat2")) rc = launch_c4<8, 2>(ctx, ax, g, sp, st);
             else if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
             else if (hi_only)
@@ -2039,10 +1889,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     ar.q_tiles = d_fqt; ar.Q = d_fq; ar.n_q = n_fail; ar.active = nullptr; ar.theta = d_ftheta;
                     ar.n_split = (int)rs; ar.cbuf = d_rbuf; ar.cap = rcap;
                     ar.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_rbuf) + nb);
-                    if (quad)
-                        rc = compact ? launch_quad<false, true>(ctx, ar, fg, rs, st) : launch_quad<false>(ctx, ar, fg, rs, st);
-                    else
-                        rc = compact ? launch_scan<MODE_COLLECT, false, 1, true>(ctx, ar, fg, rs, st)
+                    rc = compact ? launch_scan<MODE_COLLECT, false, 1, true>(ctx, ar, fg, rs, st)
                                      : launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st);
                     if (rc) return rc;
                     const int parts = 4 * (int)rs;

@@ -65,19 +65,33 @@ def compress_audio_arrays(signal, tile_size=1024, emb_dim=16, energy_thresh=1e-4
     energy_thresh, original_len)."""
     signal = np.ascontiguousarray(signal, dtype=np.float32)
     range_size, domain_step = _lib.geometry(tile_size)
-    ranges, original_len = frame_ranges(signal, range_size, energy_thresh)
     n_domains = _lib.count_domains(len(signal), tile_size, domain_step)
-    if ranges is None or n_domains == 0:
-        out = _empty_result(range_size, tile_size, domain_step, energy_thresh, original_len)
-        return (MatchArrays.from_any([]),) + out[1:]
+    original_len = len(signal)
+    empty = (MatchArrays.from_any([]),) + _empty_result(range_size, tile_size, domain_step, energy_thresh, original_len)[1:]
     if query_mode is None:
         query_mode = 1 if os.environ.get("FWAV_QUERY_MODE", "reference") == "range" else 0
-    ctx = ctx or _lib.default_context(_device())
-    res = ctx.compress_host(signal, ranges, tile_size, emb_dim, top_k if k is None else k,
-                            energy_thresh, fast_mode, query_mode)
+    kk = top_k if k is None else k
+    if not (signal[:4096].any() or signal.any()):
+        return empty       # digital silence: every frame energy is 0, the gate never opens (fractal.py:1083-1093)
+    if n_domains > 0 and original_len >= 10 * range_size:
+        # the usual case: the raw signal goes to the device once; voiced gate, masking, reflect padding and framing
+        # (fractal.py:880-909, :1074-1112) run there, bit-identical to the host pre-step
+        ctx = ctx or _lib.default_context(_device())
+        res = ctx.compress_signal_host(signal, tile_size, emb_dim, kk, energy_thresh, fast_mode, query_mode)
+        if res is None:
+            return empty
+        n_ranges = len(res["idx"])
+    else:
+        # inputs of a few frames (np.convolve's 'same' mode changes shape below five frames) or without a single
+        # domain: the host pre-step decides what the reference would return
+        ranges, original_len = frame_ranges(signal, range_size, energy_thresh)
+        if ranges is None or n_domains == 0:
+            return empty
+        ctx = ctx or _lib.default_context(_device())
+        res = ctx.compress_host(signal, ranges, tile_size, emb_dim, kk, energy_thresh, fast_mode, query_mode)
+        n_ranges = len(ranges)
     m = MatchArrays(res["idx"], res["s"], res["o"], res["sym"], res["err"])
-    return (m, res["domains"], len(ranges), range_size, tile_size, domain_step, energy_thresh,
-            original_len)
+    return (m, res["domains"], n_ranges, range_size, tile_size, domain_step, energy_thresh, original_len)
 
 
 def compress_audio(signal, framerate, sampwidth, tile_size=1024, emb_dim=16, top_k=top_k, ef_search=50,

@@ -59,6 +59,9 @@ SIGNATURES = [
                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     ("fwav_compress_host", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                      C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_prepare_ranges", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_double, c_ptr, c_ptr, c_ptr]),
+    ("fwav_compress_signal_host", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.POINTER(C.c_int)]),
     ("fwav_decode_host", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int, C.c_int,
                                    C.c_double, C.c_double, C.c_double, c_ptr,
                                    C.POINTER(C.c_int), C.POINTER(C.c_float)]),
@@ -72,6 +75,29 @@ SIGNATURES = [
 
 _lib = None
 _lock = threading.Lock()
+
+# page-locked blocks waiting for reuse: {(pid, nbytes): [address, ...]} (a forked child must not touch its parent's)
+_POOL = {}
+_POOL_PER_SIZE = 2
+_POOL_MAX_IDLE = 8 << 30
+
+
+def _pool_take(nbytes):
+    with _lock:
+        lst = _POOL.get((os.getpid(), nbytes))
+        return lst.pop() if lst else None
+
+
+def _pool_give(lib, pid, nbytes, addr):
+    if pid != os.getpid():
+        return
+    with _lock:
+        lst = _POOL.setdefault((pid, nbytes), [])
+        idle = sum(k[1] * len(v) for k, v in _POOL.items() if k[0] == pid)
+        if len(lst) < _POOL_PER_SIZE and idle + nbytes <= _POOL_MAX_IDLE:
+            lst.append(addr)
+            return
+    lib.fwav_host_free(None, addr)
 
 
 def load_library():
@@ -215,23 +241,25 @@ class Context:
 
     # ---- host-buffer entry points (what fractal.compress_audio / decompress_audio call) ----
     def pinned_empty(self, shape, dtype):
-        """numpy array in page-locked host memory (freed when the array and its views are gone) when
-        FWAV_PINNED=1, else a plain pageable one.  Opt-in: page-locking fresh memory on every call costs more
-        than the staged copies it avoids (config 2 through compress_audio_arrays on B200: 290-510 ms per call
-        with per-call pinned buffers against 148 ms with pageable ones; fwav_compress_host on buffers that are
-        pinned ONCE and reused takes 79.5 ms).  Callers that keep their buffers should allocate them once with
-        this and pass them as `out=`."""
+        """numpy array in page-locked host memory, so that it can be the end point of an asynchronous copy (the
+        domain table then downloads beside the search).  Page-locking fresh memory costs more than the staged copy
+        it avoids (config 2: 290-510 ms per call against 148 ms), so the blocks are POOLED: when the array and its
+        views are gone the block goes back to a per-process pool and the next call of the same size reuses it
+        (steady state: no allocation).  FWAV_PINNED=0 returns plain pageable arrays (the C side then stages
+        them through its own ring)."""
         dtype = np.dtype(dtype)
         shape = (shape,) if np.isscalar(shape) else tuple(shape)
         nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        if nbytes == 0 or os.environ.get("FWAV_PINNED", "0") != "1":
+        if nbytes == 0 or os.environ.get("FWAV_PINNED", "1") == "0":
             return np.empty(shape, dtype)
-        p = c_ptr()
-        if self.lib.fwav_host_alloc(self.h, nbytes, C.byref(p)) != 0 or not p.value:
-            return np.empty(shape, dtype)
-        buf = (C.c_ubyte * nbytes).from_address(p.value)
-        lib, addr = self.lib, p.value
-        weakref.finalize(buf, lib.fwav_host_free, None, addr)   # numpy keeps `buf` alive through .base
+        addr = _pool_take(nbytes)
+        if addr is None:
+            p = c_ptr()
+            if self.lib.fwav_host_alloc(self.h, nbytes, C.byref(p)) != 0 or not p.value:
+                return np.empty(shape, dtype)
+            addr = p.value
+        buf = (C.c_ubyte * nbytes).from_address(addr)
+        weakref.finalize(buf, _pool_give, self.lib, os.getpid(), nbytes, addr)   # numpy keeps `buf` alive through .base
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def compress_host(self, signal, ranges, tile_size, emb_dim, top_k, energy_thresh, fast_mode=True,
@@ -252,6 +280,32 @@ class Context:
             float(energy_thresh), int(bool(fast_mode)), int(query_mode), _hp(out["domains"]),
             _hp(out["idx"]), _hp(out["s"]), _hp(out["o"]), _hp(out["sym"]), _hp(out["err"])))
         return out
+
+    def compress_signal_host(self, signal, tile_size, emb_dim, top_k, energy_thresh, fast_mode=True,
+                             query_mode=0, want_domains=True, want_ranges=False, out=None):
+        """compress from the raw signal (device pre-step).  Returns the dict of compress_host (+ "ranges" on
+        request), or None when the reference would return its empty result for a silent input."""
+        signal = _as(signal, np.float32)
+        rs, ds = geometry(tile_size)
+        n_r = -(-len(signal) // rs)
+        n_d = count_domains(len(signal), tile_size, ds)
+        if out is None:
+            pe = self.pinned_empty
+            out = dict(
+                domains=pe((n_d, rs), np.float32) if want_domains else None,
+                ranges=pe((n_r, rs), np.float32) if want_ranges else None,
+                idx=pe(n_r, np.int32), s=pe(n_r, np.float32), o=pe(n_r, np.float32),
+                sym=pe(n_r, np.uint8), err=pe(n_r, np.float32))
+        silent = C.c_int(0)
+        self._check(self.lib.fwav_compress_signal_host(
+            self.h, _hp(signal), len(signal), int(tile_size), int(emb_dim), int(top_k), float(energy_thresh),
+            int(bool(fast_mode)), int(query_mode), _hp(out.get("ranges")), _hp(out.get("domains")),
+            _hp(out["idx"]), _hp(out["s"]), _hp(out["o"]), _hp(out["sym"]), _hp(out["err"]), C.byref(silent)))
+        return None if silent.value else out
+
+    def prepare_ranges(self, d_signal, n, range_size, energy_thresh, d_ranges, d_sumsq, stream=None):
+        self._check(self.lib.fwav_prepare_ranges(self.h, d_signal, n, int(range_size), float(energy_thresh),
+                                                 d_ranges, d_sumsq, stream))
 
     def decode_host(self, domains, idx, s, o, sym, range_size, iterations=8, convergence_eps=1e-3,
                     s_clip=16.0, s_damping=0.0, out=None):

@@ -163,6 +163,27 @@ int fwav_compress_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples,
                        float *h_domains,
                        int32_t *h_idx, float *h_s, float *h_o, uint8_t *h_sym, float *h_err);
 
+/* A0 / row N2 -- replaces voiced_detection + masking + reflect padding + framing (fractal.py:880-909, :1074-1112)
+ * on the device: d_ranges receives ceil(n_samples / range_size) * range_size floats (the gated signal with its
+ * reflected tail, i.e. the (n_ranges, range_size) array of :1112, bit-identical to the reference's), d_sumsq[0]
+ * (device, float64) the sum of squares of the gated signal that decides the "silent input" early-out of :1083.
+ * Needs at least five frames of 2 * range_size samples. */
+int fwav_prepare_ranges(fwav_ctx *ctx, const float *d_signal, int64_t n_samples, int range_size,
+                        double energy_thresh, float *d_ranges, double *d_sumsq, void *stream);
+
+/* compress_audio from the RAW signal (what fractal.compress_audio calls): fwav_prepare_ranges on the device, then
+ * the pipeline of fwav_compress_host; n_ranges = ceil(n_samples / range_size).  h_ranges (may be NULL) receives
+ * the framed ranges.  *silent is set to 1, and no output is written, when the reference returns its empty result
+ * for a silent input (:1083-1093).  Pageable buffers are staged through a context-owned page-locked ring in 8 MB
+ * chunks (upload on the calling thread, download of the domain table on a helper thread beside the search);
+ * page-locked buffers (fwav_host_alloc) are the end points of the asynchronous copies themselves. */
+int fwav_compress_signal_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples,
+                              int tile_size, int emb_dim, int top_k, double energy_thresh,
+                              int fast_mode, int query_mode,
+                              float *h_ranges, float *h_domains,
+                              int32_t *h_idx, float *h_s, float *h_o, uint8_t *h_sym, float *h_err,
+                              int *silent);
+
 /* Host-buffer decoder (what decompress_audio calls). h_out: n_ranges*range_size. */
 int fwav_decode_host(fwav_ctx *ctx, const float *h_domains, int64_t n_domains,
                      const int32_t *h_idx, const float *h_s, const float *h_o, const uint8_t *h_sym,

@@ -5,7 +5,7 @@
 set +e
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,temperature.gpu --format=csv > $O/r02a_smi.txt
-for lay in fat quad sets; do
+for lay in thin4 thin2 fat4 fat2 sets; do
   timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "collect_layouts and $lay" > $O/r02a_layout_$lay.txt 2>&1
   echo "layout $lay: rc=$? $(tail -1 $O/r02a_layout_$lay.txt)"
 done
@@ -17,7 +17,7 @@ FWAV_TEST_EXPERIMENTAL=1 timeout 1200 python -m pytest tests -m gpu -q --duratio
 echo "full suite: rc=$? $(tail -1 $O/r02a_pytest.txt)"
 # ---- timings: the search alone on config 2, three repetitions each ----
 rm -f $O/r02a_timing.txt
-for lay in sets fat quad; do
+for lay in sets thin4 thin2 fat4 fat2; do
   echo "== FWAV_UMMA_COLLECT=$lay (config 2)" >> $O/r02a_timing.txt
   FWAV_UMMA_COLLECT=$lay FWAV_UMMA_VERBOSE=1 timeout 200 python scripts/time_topk.py 1.0 umma 3 > $O/r02a_t.out 2> $O/r02a_t.err
   grep "fwav\]" $O/r02a_t.err | tail -3 | cut -c1-220 >> $O/r02a_timing.txt

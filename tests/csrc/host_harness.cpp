@@ -136,4 +136,36 @@ int hh_decode(const float *domains, const int32_t *idx, const float *s, const fl
 
 float hh_score(const float *q, const float *e, int dim) { return fwm::score_chain(q, e, dim); }
 
+// pre-step (A0 / N2) with the device's per-frame functions and the reference's sequential gate:
+// mask (n bytes), ranges (ceil(n / N) * N floats), returns the float64 sum of squares of the gated signal
+double hh_prestep(const float *sig, long long n, int N, double thr, uint8_t *mask, float *ranges) {
+    const int fs = 2 * N;
+    const long long n_frames = (n + fs - 1) / fs;
+    auto s = [&](long long i) { return sig[i]; };
+    std::vector<float> energy(n_frames);
+    for (long long f = 0; f < n_frames; ++f) {
+        if (fs == 8) energy[f] = fwm::frame_energy<8>(s, f, fs, n);
+        else if (fs == 32) energy[f] = fwm::frame_energy<32>(s, f, fs, n);
+        else energy[f] = fwm::frame_energy(s, f, fs, n);
+    }
+    auto e = [&](long long j) { return energy[j]; };
+    std::vector<uint8_t> gate(n_frames);
+    long long run = -1;                       // running maximum of the keys, as the device scan computes it
+    for (long long f = 0; f < n_frames; ++f) {
+        const long long k = fwm::gate_key(fwm::smooth5(e, f, n_frames), f, thr);
+        if (k > run) run = k;
+        gate[f] = run >= 0 && (run & 1);
+    }
+    for (long long i = 0; i < n; ++i) mask[i] = gate[i / fs];
+    const long long n_out = (n + N - 1) / N * N;
+    double ssq = 0.0;
+    for (long long i = 0; i < n_out; ++i) {
+        const long long src = fwm::reflect_index(i, n);
+        const float v = npm::mul(sig[src], gate[src / fs] ? 1.0f : 0.0f);
+        ranges[i] = v;
+        if (i < n) ssq += (double)v * (double)v;
+    }
+    return ssq;
+}
+
 }  // extern "C"

@@ -29,6 +29,7 @@ def load():
     lib.hh_np_mean.restype = C.c_float
     lib.hh_score.restype = C.c_float
     lib.hh_decode.restype = C.c_int
+    lib.hh_prestep.restype = C.c_double
     return lib
 
 
@@ -43,6 +44,14 @@ def f32(a):
 class Harness:
     def __init__(self):
         self.lib = load()
+
+    def prestep(self, sig, N, thr=1e-4):
+        sig = f32(sig)
+        n = len(sig)
+        mask = np.empty(n, np.uint8)
+        ranges = np.empty((-(-n // N), N), np.float32)
+        ssq = self.lib.hh_prestep(_p(sig), C.c_longlong(n), C.c_int(N), C.c_double(thr), _p(mask), _p(ranges))
+        return mask, ranges, float(ssq)
 
     def np_mean(self, a):
         a = f32(a)

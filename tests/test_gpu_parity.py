@@ -505,7 +505,7 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
 
 
-@pytest.mark.parametrize("layout", ["fat", "quad", "sets"])
+@pytest.mark.parametrize("layout", ["thin4", "thin2", "fat4", "fat2", "sets"])
 @pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None),
                                             (20000, 32, "hionly")])
 def test_collect_layouts(ctx, monkeypatch, layout, n_q, top_k, mode):
@@ -544,7 +544,7 @@ def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
     """Embeddings shaped like range_size 4 (3 live tonal + 4 live transient dimensions, the rest exactly zero):
     the two-MMA compact split must return what the FFMA kernel returns."""
     monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
-    monkeypatch.setenv("FWAV_UMMA_COLLECT", "quad" if quad == "1" else "sets")
+    monkeypatch.setenv("FWAV_UMMA_COLLECT", "thin4" if quad == "1" else "sets")
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     ED = 16
@@ -658,8 +658,8 @@ def _music_table(ctx, seconds, seed, tile=4096, N=16, ds=4, ED=16):
     return n_d, d_emb, d_emb.to_host((n_d, ED), np.float32)
 
 
-@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "fat"), (32, 48, "fat"), (32, None, "sets"), (64, None, "fat"),
-                                              (64, 48, "fat")])
+@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "thin4"), (32, 48, "thin4"), (32, None, "sets"), (32, 48, "fat4"),
+                                              (64, None, "thin4"), (64, 48, "thin4")])
 def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
     """The fast path works in batches of 2^20 queries (configs 3 and 4 run 2-21 of them per rank).  FWAV_UMMA_BATCH
     shrinks the batch so that a 5 000-query search crosses batch boundaries seven times: with a pruning mask, a split
@@ -862,6 +862,77 @@ def test_forged_indices_are_rejected_not_dereferenced(ctx):
     # the context survived all of it
     out, iters, _ = ctx.decode_host(g["domains"], g["idx"], g["s"], g["o"], g["sym"], N)
     assert np.array_equal(bits(out[:len(g["dec_default"])]), bits(g["dec_default"]))
+
+
+# ------------------------------------------------------------------ row N2: the pre-step on the device
+def _device_ranges(ctx, sig, N, thr=1e-4):
+    sig = np.ascontiguousarray(sig, np.float32)
+    n_r = -(-len(sig) // N)
+    d_sig, d_rng, d_sum = ctx.upload(sig), ctx.alloc(n_r * N * 4), ctx.alloc(8)
+    ctx.prepare_ranges(d_sig.ptr, len(sig), N, thr, d_rng.ptr, d_sum.ptr)
+    return d_rng.to_host((n_r, N), np.float32), float(d_sum.to_host(1, np.float64)[0])
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_prestep_device_bit_exact(ctx, name):
+    """Voiced gate + masking + reflect padding + framing on the device against the ranges the REFERENCE framed."""
+    g = golden(name)
+    got, ssq = _device_ranges(ctx, g["signal"], int(g["range_size"]), float(g["energy_thresh"]))
+    assert np.array_equal(bits(got), bits(g["ranges"]))
+    assert ssq >= 1e-8
+
+
+def test_prestep_device_gate_scan_and_edges(ctx):
+    from fwav_b200.prestep import frame_ranges, voiced_detection
+    g = golden("voiced")
+    got, _ = _device_ranges(ctx, g["signal"], 4)
+    assert np.array_equal(got.ravel()[:8000] != 0, (g["signal"] * g["mask_f8"]) != 0)
+    got, _ = _device_ranges(ctx, g["signal"] * 1e-4, 16)
+    want, _ = frame_ranges((g["signal"] * 1e-4).astype(np.float32), 16, 1e-4)
+    assert np.array_equal(bits(got), bits(want))
+    # long signals: the hysteresis state crosses many 1024-frame scan blocks (and the second scan level), with
+    # stretches where the smoothed energy sits between the two thresholds and the previous state must carry over
+    rng = np.random.default_rng(21)
+    for N, n in [(4, 3_000_017), (16, 9_000_001), (11, 1_234_567)]:
+        env = np.repeat(rng.choice([0.0, 0.0, 8e-3, 1.0], size=-(-n // 4000)), 4000)[:n]     # 8e-3^2 = 6.4e-5: in between
+        x = (rng.standard_normal(n) * env).astype(np.float32)
+        got, ssq = _device_ranges(ctx, x, N)
+        want, _ = frame_ranges(x, N, 1e-4)
+        assert np.array_equal(bits(got), bits(want)), (N, n)
+        mask = voiced_detection(x, 2 * N, 1e-4)
+        assert abs(ssq - float(np.sum((x * mask).astype(np.float64) ** 2))) <= 1e-9 * ssq
+
+
+@pytest.mark.parametrize("pinned", ["1", "0"])
+def test_compress_from_the_raw_signal(ctx, monkeypatch, pinned):
+    """fwav_compress_signal_host (device pre-step; page-locked pooled outputs, or pageable ones staged through the
+    context's ring by the helper thread) returns what fwav_compress_host returns for host-framed ranges."""
+    from fwav_b200 import synth
+    monkeypatch.setenv("FWAV_PINNED", pinned)
+    for name in ("music_t4096", "gaps_t1024", "sine_t1100"):
+        g = golden(name)
+        tile, K = int(g["tile_size"]), int(g["top_k"])
+        a = ctx.compress_host(g["signal"], g["ranges"], tile, 16, K, 1e-4)
+        b = ctx.compress_signal_host(g["signal"], tile, 16, K, 1e-4, want_ranges=True)
+        assert np.array_equal(bits(b["ranges"]), bits(g["ranges"]))
+        for k in ("domains", "s", "o", "err"):
+            assert np.array_equal(bits(a[k]), bits(b[k])), (name, k)
+        assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["sym"], b["sym"])
+    # a table larger than the ring (4 x 8 MB): 40 s of config 2's signal, 28 MB of domains
+    sig = synth.music_like(seconds=40.0, rate=44100, seed=2)
+    from fwav_b200.prestep import frame_ranges
+    ranges, _ = frame_ranges(sig, 16, 1e-4)
+    a = ctx.compress_host(sig, ranges, 4096, 16, 32, 1e-4)
+    b = ctx.compress_signal_host(sig, 4096, 16, 32, 1e-4)
+    for k in ("domains", "s", "o", "err"):
+        assert np.array_equal(bits(a[k]), bits(b[k])), k
+    assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["sym"], b["sym"])
+    # a signal whose gate never opens: the reference's empty result
+    quiet = (np.random.default_rng(0).standard_normal(50000) * 1e-3).astype(np.float32)
+    assert ctx.compress_signal_host(quiet, 1024, 16, 32, 1e-4) is None
+    import fractal
+    out = fractal.compress_audio(quiet, 16000, 2, tile_size=1024)
+    assert out[0] == [] and out[1].shape == (0, 4) and out[2] == 0 and out[7] == 50000
 
 
 # ------------------------------------------------------------------ the multi-GPU driver on one GPU

@@ -72,3 +72,34 @@ def test_decode_bit_exact(name):
         out, it, delta = H.decode(g["domains"], g["idx"], g["s"], g["o"], g["sym"], N, **kw)
         want = g["dec_" + tag]
         assert np.array_equal(bits(out[:len(want)]), bits(want)), tag
+
+
+def test_prestep_math_matches_the_reference_gate():
+    """Row N2: the device pre-step's per-frame math (frame energies in numpy's order, the 5-tap smoothing with its
+    two edge forms, the threshold keys whose running maximum is the hysteresis) against masks the reference's
+    voiced_detection produced, and against the host pre-step on every fixture's signal."""
+    from fwav_b200.prestep import frame_ranges, voiced_detection
+    g = golden("voiced")
+    mask, _, _ = H.prestep(g["signal"], 4)
+    assert np.array_equal(mask, g["mask_f8"])
+    mask, _, _ = H.prestep(g["signal"] * 1e-4, 16)
+    assert np.array_equal(mask, g["mask_scaled_f32"])
+    for name in ALL:
+        f = golden(name)
+        N, thr = int(f["range_size"]), float(f["energy_thresh"])
+        mask, ranges, ssq = H.prestep(f["signal"], N, thr)
+        assert np.array_equal(mask, voiced_detection(f["signal"], 2 * N, thr)), name
+        assert np.array_equal(bits(ranges), bits(f["ranges"])), name            # what the reference framed
+        assert ssq >= 1e-8
+    # float-scale signals whose energies straddle the thresholds, odd frame sizes, lengths that need the reflected tail
+    rng = np.random.default_rng(5)
+    for N, n in [(4, 1003), (5, 777), (11, 4099), (16, 10007), (32, 6400), (7, 71)]:
+        for scale in (1e-2, 3e-2, 1.0):
+            x = (rng.standard_normal(n) * scale * np.repeat(rng.random(-(-n // 50)) < 0.5, 50)[:n]).astype(np.float32)
+            mask, ranges, ssq = H.prestep(x, N, 1e-4)
+            assert np.array_equal(mask, voiced_detection(x, 2 * N, 1e-4)), (N, n, scale)
+            want, _ = frame_ranges(x, N, 1e-4)
+            if want is None:
+                assert ssq < 1e-8 or len(x) < N
+            else:
+                assert np.array_equal(bits(ranges), bits(want)), (N, n, scale)
