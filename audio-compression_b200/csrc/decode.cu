@@ -14,7 +14,14 @@
 // block that adds the partials in index order.  The convergence test runs on
 // the device; once it fires the remaining iteration launches return at once.
 //
-// Bound: HBM, 12*N + 13 bytes per range per iteration.
+// Round 2: the tiles are static (:1414 indexes the stored domain table, never the evolving reconstruction), so
+// the random 4*N-byte row gathers happen ONCE, in decode_prepare_kernel, which writes the tiles in range order
+// (mirrored and zeroed as :1417-1429 ask) together with the s / o the iteration will use.  Every iteration then
+// streams three contiguous arrays (tiles, current and next reconstruction): a warp moves 32 ranges as whole
+// 512-byte lines and hands each lane its own range through a padded shared-memory transpose.  Range sizes outside
+// {4, 8, 16, 32} keep the direct kernel.
+//
+// Bound: HBM, 12*N + 13 bytes per range per iteration; the streaming kernel moves 12*N + 8.
 #include "common.cuh"
 #include "fwav_math.cuh"
 
@@ -113,6 +120,151 @@ decode_iter_kernel(const float *__restrict__ domains, const int32_t *__restrict_
     }
 }
 
+
+// ---- round 2: gather once, stream every iteration ----
+template <int NT>
+__global__ void __launch_bounds__(kThreads)
+decode_prepare_kernel(const float *__restrict__ domains, long long n_d, const int32_t *__restrict__ idx,
+                      const float *__restrict__ s_st, const float *__restrict__ o_st, const uint8_t *__restrict__ sym,
+                      long long n_r, float *__restrict__ tiles, float *__restrict__ s_use, float *__restrict__ o_use,
+                      DecodeState *__restrict__ state) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_r; i += (long long)gridDim.x * blockDim.x) {
+        int raw = __ldg(idx + i);
+        if (raw >= n_d) {            // corrupt or forged container: never read past the table; reported by the host side
+            state->bad_index = 1;
+            raw = -1;
+        }
+        const bool dead = raw < 0;                                        // :1399-1426
+        const bool flip = !dead && __ldg(sym + i) != 0;                   // :1428-1429
+        s_use[i] = dead ? 0.0f : __ldg(s_st + i);
+        o_use[i] = dead ? 0.0f : __ldg(o_st + i);
+        const float4 *tp = reinterpret_cast<const float4 *>(domains + (long long)(dead ? 0 : raw) * NT);
+        float4 *out = reinterpret_cast<float4 *>(tiles + i * NT);
+        float4 v[NT / 4];
+#pragma unroll
+        for (int k = 0; k < NT / 4; ++k) v[k] = dead ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(tp + k);
+        if (flip) {
+#pragma unroll
+            for (int k = 0; k < NT / 4; ++k) {
+                const float4 a = v[NT / 4 - 1 - k];
+                st_stream_f4(out + k, make_float4(a.w, a.z, a.y, a.x));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NT / 4; ++k) st_stream_f4(out + k, v[k]);
+        }
+    }
+}
+
+// One iteration over the prepared tiles.  A warp takes 32 consecutive ranges per pass; tiles, current and next
+// reconstruction of those ranges are 32 * NT contiguous floats each, moved as float4 with consecutive lanes on
+// consecutive addresses, and transposed through shared memory (rows padded to NT + 4 floats: a lane's row reads
+// hit distinct banks) so that lane r holds range r for fwm::decode_range.
+template <int NT>
+__global__ void __launch_bounds__(kThreads)
+decode_stream_kernel(const float *__restrict__ tiles, const float *__restrict__ s_use, const float *__restrict__ o_use,
+                     long long n_r, float clipf, int damped, float one_minus_damp, float damp, int first,
+                     const float *__restrict__ cur, float *__restrict__ nxt, const DecodeState *__restrict__ state,
+                     double *__restrict__ partials) {
+    if (state->done) return;
+    constexpr int V = NT / 4;                   // float4 per range
+    constexpr int kRow = NT + 4;                // padded row, in floats
+    __shared__ __align__(16) float sh[kThreads / 32][32 * kRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *my = sh[warp];
+    const long long n_groups = (n_r + 31) / 32;
+    const long long total4 = n_r * V;
+    double dsq = 0.0, csq = 0.0;
+    for (long long g = blockIdx.x * (long long)(kThreads / 32) + warp; g < n_groups; g += (long long)gridDim.x * (kThreads / 32)) {
+        const long long base4 = g * 32 * V;     // first float4 of the group in each array
+        const long long i = g * 32 + lane;      // this lane's range
+        float t[NT], c[NT], w[NT];
+        // coalesced loads: all of them in flight before the first shared-memory store
+        float4 vt[V], vc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const long long j = base4 + k * 32 + lane;
+            vt[k] = j < total4 ? ld_stream_f4(reinterpret_cast<const float4 *>(tiles) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vc[k] = (!first && j < total4) ? ld_stream_f4(reinterpret_cast<const float4 *>(cur) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float sv = i < n_r ? __ldg(s_use + i) : 0.0f, ov = i < n_r ? __ldg(o_use + i) : 0.0f;
+        if (V == 1) {                           // range_size 4: a lane's float4 already is its range
+            t[0] = vt[0].x; t[1] = vt[0].y; t[2] = vt[0].z; t[3] = vt[0].w;
+            c[0] = vc[0].x; c[1] = vc[0].y; c[2] = vc[0].z; c[3] = vc[0].w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int f = k * 32 + lane;    // float4 number f of the group: row f / V, column f % V
+                *reinterpret_cast<float4 *>(my + (f / V) * kRow + (f % V) * 4) = vt[k];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float4 a = *reinterpret_cast<const float4 *>(my + lane * kRow + k * 4);
+                t[4 * k] = a.x; t[4 * k + 1] = a.y; t[4 * k + 2] = a.z; t[4 * k + 3] = a.w;
+            }
+            __syncwarp();
+            if (!first) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const int f = k * 32 + lane;
+                    *reinterpret_cast<float4 *>(my + (f / V) * kRow + (f % V) * 4) = vc[k];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float4 a = *reinterpret_cast<const float4 *>(my + lane * kRow + k * 4);
+                    c[4 * k] = a.x; c[4 * k + 1] = a.y; c[4 * k + 2] = a.z; c[4 * k + 3] = a.w;
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) c[k] = 0.0f;
+            }
+        }
+        if (i < n_r) {
+            auto cc = [&](int k) { return c[k]; };
+            auto tt = [&](int k) { return t[k]; };
+            auto put = [&](int k, float v) { w[k] = v; };
+            fwm::decode_range<NT>(cc, tt, sv, ov, NT, clipf, damped != 0, one_minus_damp, damp, put, &dsq, &csq);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NT; ++k) w[k] = 0.0f;
+        }
+        if (V == 1) {
+            if (i < n_r) st_stream_f4(reinterpret_cast<float4 *>(nxt) + base4 + lane, make_float4(w[0], w[1], w[2], w[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                *reinterpret_cast<float4 *>(my + lane * kRow + k * 4) = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int f = k * 32 + lane;
+                const long long j = base4 + f;
+                if (j < total4) st_stream_f4(reinterpret_cast<float4 *>(nxt) + j, *reinterpret_cast<const float4 *>(my + (f / V) * kRow + (f % V) * 4));
+            }
+            __syncwarp();
+        }
+    }
+    // fixed-order block reduction of the two float64 sums
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        dsq += __shfl_down_sync(kFull, dsq, off);
+        csq += __shfl_down_sync(kFull, csq, off);
+    }
+    __shared__ double red[2][kThreads / 32];
+    if (lane == 0) { red[0][warp] = dsq; red[1][warp] = csq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < kThreads / 32; ++wq) { a += red[0][wq]; b += red[1][wq]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
 __global__ void __launch_bounds__(32)
 decode_finalize_kernel(const double *__restrict__ partials, int n_blocks, double eps,
                        DecodeState *__restrict__ state) {
@@ -158,6 +310,57 @@ decode_sum_partials_kernel(const double *__restrict__ partials, int n_blocks, do
 
 }  // namespace
 
+namespace {
+
+// the prepared form of a decode: tiles in range order + the s / o each range uses (see decode_prepare_kernel)
+struct Prepared {
+    float *tiles = nullptr, *s_use = nullptr, *o_use = nullptr;
+};
+
+bool streamable(int N, const void *a, const void *b, const void *c) {
+    return (N == 4 || N == 8 || N == 16 || N == 32) &&
+           ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
+int prepared_buffers(fwav_ctx *ctx, int64_t n_r, int N, Prepared *p) {
+    const size_t sz_t = ((size_t)n_r * N * 4 + 255) & ~(size_t)255, sz_v = ((size_t)n_r * 4 + 255) & ~(size_t)255;
+    unsigned char *blk = nullptr;
+    int rc = fwav_ws_reserve(ctx, WS_DECODE_TILES, sz_t + 2 * sz_v, (void **)&blk);
+    if (rc) return rc;
+    p->tiles = reinterpret_cast<float *>(blk);
+    p->s_use = reinterpret_cast<float *>(blk + sz_t);
+    p->o_use = reinterpret_cast<float *>(blk + sz_t + sz_v);
+    return FWAV_OK;
+}
+
+int launch_prepare(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx, const float *d_s,
+                   const float *d_o, const uint8_t *d_sym, int64_t n_r, int N, const Prepared &p, DecodeState *d_state,
+                   int grid, cudaStream_t st) {
+#define FWAV_PREP(NT) decode_prepare_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, (long long)n_d, d_idx, d_s, d_o, d_sym, n_r, p.tiles, p.s_use, p.o_use, d_state)
+    if (N == 4) FWAV_PREP(4);
+    else if (N == 8) FWAV_PREP(8);
+    else if (N == 16) FWAV_PREP(16);
+    else FWAV_PREP(32);
+#undef FWAV_PREP
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
+int launch_stream(fwav_ctx *ctx, const Prepared &p, int64_t n_r, int N, float clipf, int damped, float omd, float dmp,
+                  int first, const float *cur, float *nxt, const DecodeState *d_state, double *d_part, int grid,
+                  cudaStream_t st) {
+#define FWAV_STRM(NT) decode_stream_kernel<NT><<<grid, kThreads, 0, st>>>(p.tiles, p.s_use, p.o_use, n_r, clipf, damped, omd, dmp, first, cur, nxt, d_state, d_part)
+    if (N == 4) FWAV_STRM(4);
+    else if (N == 8) FWAV_STRM(8);
+    else if (N == 16) FWAV_STRM(16);
+    else FWAV_STRM(32);
+#undef FWAV_STRM
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
+}  // namespace
+
 // One decoder iteration over a slice of ranges (multi-GPU decode: every rank owns a
 // slice, the two float64 sums are combined across ranks by the caller).
 int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
@@ -183,6 +386,18 @@ int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, 
     const float omd = (float)(1.0 - s_damping), dmp = (float)s_damping;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_domains) | reinterpret_cast<uintptr_t>(d_cur) |
                            reinterpret_cast<uintptr_t>(d_next)) & 15) == 0;
+    if (streamable(N, d_domains, d_cur, d_next)) {
+        // the first call of a decode gathers the tiles into the context's workspace; the calls that follow
+        // (first == 0, same matches) stream them
+        Prepared p;
+        if ((rc = prepared_buffers(ctx, n_r, N, &p))) return rc;
+        if (first && (rc = launch_prepare(ctx, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, N, p, d_state, grid, st))) return rc;
+        const int sgrid = (int)(((n_r + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32) < cap ? ((n_r + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32) : cap);
+        if ((rc = launch_stream(ctx, p, n_r, N, clipf, damped, omd, dmp, first, d_cur, d_next, d_state, d_part, sgrid, st))) return rc;
+        decode_sum_partials_kernel<<<1, 32, 0, st>>>(d_part, sgrid, d_sums);
+        FWAV_LAUNCH_CHECK(ctx);
+        return FWAV_OK;
+    }
 #define FWAV_DEC(NT)                                                                                   \
     decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
                                                       damped, omd, dmp, first, d_cur, d_next, d_state, d_part, (long long)n_d)
@@ -233,9 +448,24 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
                            reinterpret_cast<uintptr_t>(d_scratch)) & 15) == 0;
     // iteration `it` reads buf[it & 1] and writes buf[(it + 1) & 1]; buf[0] is d_out
     float *buf[2] = {d_out, d_scratch};
+    const bool stream = streamable(N, d_domains, d_out, d_scratch);
+    Prepared prep;
+    int sgrid = grid;
+    if (stream) {
+        if ((rc = prepared_buffers(ctx, n_r, N, &prep))) return rc;
+        if ((rc = launch_prepare(ctx, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, N, prep, d_state, grid, st))) return rc;
+        const long long sneed = ((n_r + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32);
+        sgrid = (int)(sneed < cap ? sneed : cap);
+    }
     for (int it = 0; it < iterations; ++it) {
         const float *cur = buf[it & 1];
         float *nxt = buf[(it + 1) & 1];
+        if (stream) {
+            if ((rc = launch_stream(ctx, prep, n_r, N, clipf, damped, omd, dmp, it == 0, cur, nxt, d_state, d_part, sgrid, st))) return rc;
+            decode_finalize_kernel<<<1, 32, 0, st>>>(d_part, sgrid, eps, d_state);
+            FWAV_LAUNCH_CHECK(ctx);
+            continue;
+        }
 #define FWAV_DEC(NT)                                                                               \
     decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
                                                       damped, omd, dmp, it == 0, cur, nxt, d_state, d_part, (long long)n_d)

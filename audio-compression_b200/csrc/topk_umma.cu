@@ -1043,7 +1043,9 @@ __device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_de
 // (2 * set, 2 * set + 1) laid end to end.  finalize_kernel reads the parts as before.
 // ---------------------------------------------------------------------------
 __host__ __device__ constexpr int c4_threads(int epi, int iss) { return (epi + 1 + iss) * 32; }
-__host__ __device__ constexpr int c4_regs(int epi, int iss) { return epi == 16 ? 96 : (iss == 4 ? 152 : 168); }
+// registers are split four ways (one file of 16 K per scheduler): 16 + 1 + 3 = 20 warps of 96 registers are five
+// per scheduler, 8 + 1 + 3 = 12 warps of 168 are three; a fourth issuer warp does not fit either layout
+__host__ __device__ constexpr int c4_regs(int epi, int iss) { return epi == 16 ? 96 : 168; }
 constexpr uint32_t kC4OffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
 __host__ __device__ constexpr uint32_t c4_smem(int epi) { return kC4OffStage + (uint32_t)epi * 8 * 32 * 4; }
 
@@ -1676,7 +1678,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
     // layout of the hi*hi-only collect pass: "sets" (scan_kernel: two 256-column buffers, two epilogue sets) or
-    // collect4_kernel as "thin4" / "thin2" / "fat4" / "fat2" (epilogue layout, issuer threads); all return the same
+    // collect4_kernel as "thin3" / "thin2" / "fat3" / "fat2" (epilogue layout, issuer threads); all return the same
     const char *layout_env = getenv("FWAV_UMMA_COLLECT");
     const char *layout = single ? (layout_env ? layout_env : kDefaultCollect) : "sets";
     long long batch_cap = kBatchQueries;
@@ -1788,9 +1790,9 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
-            if (hi_only && !strcmp(layout, "thin4")) rc = launch_c4<16, 4>(ctx, ax, g, sp, st);
+            if (hi_only && !strcmp(layout, "thin3")) rc = launch_c4<16, 3>(ctx, ax, g, sp, st);
             else if (hi_only && !strcmp(layout, "thin2")) rc = launch_c4<16, 2>(ctx, ax, g, sp, st);
-            else if (hi_only && !strcmp(layout, "fat4")) rc = launch_c4<8, 4>(ctx, ax, g, sp, st);
+            else if (hi_only && !strcmp(layout, "fat3")) rc = launch_c4<8, 3>(ctx, ax, g, sp, st);
             else if (hi_only && !strcmp(layout, "fat2")) rc = launch_c4<8, 2>(ctx, ax, g, sp, st);
             else if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);

@@ -241,16 +241,16 @@ class Context:
 
     # ---- host-buffer entry points (what fractal.compress_audio / decompress_audio call) ----
     def pinned_empty(self, shape, dtype):
-        """numpy array in page-locked host memory, so that it can be the end point of an asynchronous copy (the
-        domain table then downloads beside the search).  Page-locking fresh memory costs more than the staged copy
-        it avoids (config 2: 290-510 ms per call against 148 ms), so the blocks are POOLED: when the array and its
-        views are gone the block goes back to a per-process pool and the next call of the same size reuses it
-        (steady state: no allocation).  FWAV_PINNED=0 returns plain pageable arrays (the C side then stages
-        them through its own ring)."""
+        """Output array of the host-buffer entry points.  Default: a plain pageable array -- the C side stages it
+        through the context's page-locked ring, the domain table downloading on a helper thread beside the search
+        (config 2 through compress_audio_arrays on B200: 83 ms per call against 78 ms of kernels).  FWAV_PINNED=1:
+        page-locked blocks that are the end points of the asynchronous copies themselves; page-locking fresh memory
+        costs more than it saves (290-510 ms per call), so the blocks are POOLED per process and reused by the next
+        call of the same size (91-99 ms per call: the pool still misses while the previous result is alive)."""
         dtype = np.dtype(dtype)
         shape = (shape,) if np.isscalar(shape) else tuple(shape)
         nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        if nbytes == 0 or os.environ.get("FWAV_PINNED", "1") == "0":
+        if nbytes == 0 or os.environ.get("FWAV_PINNED", "0") != "1":
             return np.empty(shape, dtype)
         addr = _pool_take(nbytes)
         if addr is None:

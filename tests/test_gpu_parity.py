@@ -505,7 +505,7 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
 
 
-@pytest.mark.parametrize("layout", ["thin4", "thin2", "fat4", "fat2", "sets"])
+@pytest.mark.parametrize("layout", ["thin3", "thin2", "fat3", "fat2", "sets"])
 @pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None),
                                             (20000, 32, "hionly")])
 def test_collect_layouts(ctx, monkeypatch, layout, n_q, top_k, mode):
@@ -544,7 +544,7 @@ def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
     """Embeddings shaped like range_size 4 (3 live tonal + 4 live transient dimensions, the rest exactly zero):
     the two-MMA compact split must return what the FFMA kernel returns."""
     monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
-    monkeypatch.setenv("FWAV_UMMA_COLLECT", "thin4" if quad == "1" else "sets")
+    monkeypatch.setenv("FWAV_UMMA_COLLECT", "thin3" if quad == "1" else "sets")
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     ED = 16
@@ -658,8 +658,8 @@ def _music_table(ctx, seconds, seed, tile=4096, N=16, ds=4, ED=16):
     return n_d, d_emb, d_emb.to_host((n_d, ED), np.float32)
 
 
-@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "thin4"), (32, 48, "thin4"), (32, None, "sets"), (32, 48, "fat4"),
-                                              (64, None, "thin4"), (64, 48, "thin4")])
+@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "thin3"), (32, 48, "thin3"), (32, None, "sets"), (32, 48, "fat3"),
+                                              (64, None, "thin3"), (64, 48, "thin3")])
 def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
     """The fast path works in batches of 2^20 queries (configs 3 and 4 run 2-21 of them per rank).  FWAV_UMMA_BATCH
     shrinks the batch so that a 5 000-query search crosses batch boundaries seven times: with a pruning mask, a split
