@@ -108,7 +108,9 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
 int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
                             const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
                             double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
-                            double *d_sums, cudaStream_t st);
+                            double *d_sums, void *d_user_state, cudaStream_t st);
+int fwav_launch_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double eps, void *d_state,
+                                cudaStream_t st);
 
 #if defined(__CUDACC__)
 // streaming loads/stores that do not pollute L1 (data touched once)

@@ -285,6 +285,19 @@ decode_finalize_kernel(const double *__restrict__ partials, int n_blocks, double
     }
 }
 
+// range-sharded decode: the per-rank sums of one iteration, added in RANK ORDER (bit-stable for a given world size),
+// then the same bookkeeping as decode_finalize_kernel -- the convergence decision stays on the device
+__global__ void decode_converge_kernel(const double *__restrict__ sums_all, int n_parts, double eps,
+                                       DecodeState *__restrict__ state) {
+    if (state->done) return;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < n_parts; ++r) { a += sums_all[2 * r]; b += sums_all[2 * r + 1]; }
+    const float delta = fwm::decode_delta(a, b);                         // :1460-1461
+    state->delta = delta;
+    state->iters_run += 1;
+    if ((double)delta < eps) state->done = 1;                            // :1465
+}
+
 template <class T>
 __global__ void __launch_bounds__(256)
 decode_select_kernel(const DecodeState *__restrict__ state, const T *__restrict__ scratch,
@@ -366,7 +379,7 @@ int launch_stream(fwav_ctx *ctx, const Prepared &p, int64_t n_r, int N, float cl
 int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
                             const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
                             double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
-                            double *d_sums, cudaStream_t st) {
+                            double *d_sums, void *d_user_state, cudaStream_t st) {
     FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
     if (n_r == 0) {
         FWAV_CUDA(ctx, cudaMemsetAsync(d_sums, 0, 2 * sizeof(double), st));
@@ -380,7 +393,10 @@ int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, 
     int rc = fwav_ws_reserve(ctx, WS_DECODE_RED, sizeof(double) * 2 * (size_t)cap + sizeof(DecodeState), (void **)&d_part);
     if (rc) return rc;
     DecodeState *d_state = reinterpret_cast<DecodeState *>(d_part + 2 * (size_t)cap);
-    FWAV_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(DecodeState), st));
+    if (d_user_state)
+        d_state = static_cast<DecodeState *>(d_user_state);      // the caller's: its `done` flag gates this launch
+    else
+        FWAV_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(DecodeState), st));
     const float clipf = (float)fabs(s_clip);
     const int damped = s_damping > 0 ? 1 : 0;
     const float omd = (float)(1.0 - s_damping), dmp = (float)s_damping;
@@ -492,5 +508,13 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
     if (iters_run) *iters_run = h.iters_run;
     if (last_delta) *last_delta = h.delta;
     FWAV_REQUIRE(ctx, !h.bad_index, "index out of bounds: a match points past the %lld-row domain table", (long long)n_d);
+    return FWAV_OK;
+}
+
+int fwav_launch_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double eps, void *d_state,
+                                cudaStream_t st) {
+    static_assert(sizeof(DecodeState) == sizeof(fwav_decode_state), "fwav_decode_state is the device-side DecodeState");
+    decode_converge_kernel<<<1, 1, 0, st>>>(d_sums_all, n_parts, eps, static_cast<DecodeState *>(d_state));
+    FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }

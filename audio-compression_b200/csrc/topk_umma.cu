@@ -90,7 +90,8 @@ constexpr int kThetaWarm = 24;         // first stages of pass 1 that only look 
 constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
 // MODE_THETA: [row][3][kThetaPart] scores of column groups 1..3 for the final merge
 __host__ __device__ constexpr uint32_t mode_bytes(int mode) {
-    return mode == MODE_LISTS ? (kOffScratch - kOffMode) + 8 * 128 * 4 : mode == MODE_THETA ? kQTile * 3 * kThetaPart * 4 : 0;
+    // MODE_COLLECT: [warp][slot 0..7][lane] candidate indices staged for whole-sector stores (16 warps x 1 KB)
+    return mode == MODE_LISTS ? (kOffScratch - kOffMode) + 8 * 128 * 4 : mode == MODE_THETA ? kQTile * 3 * kThetaPart * 4 : 16 * 8 * 32 * 4;
 }
 __host__ __device__ constexpr uint32_t off_ring(int mode) { return (kOffMode + mode_bytes(mode) + 1023u) & ~1023u; }
 // a stage is 256 domains: one 8 KB tile per CTA of a pair, or both tiles (16 KB) in a CTA on its own
@@ -248,6 +249,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : FWAV_R32(v), FWAV_R32(w)
+        : "r"(taddr)
+        : "memory");
+}
+
 // wait for the loads; the registers are threaded through so no use can be scheduled above it
 __device__ __forceinline__ void tmem_wait_ld1(uint32_t (&a)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a)::"memory");
@@ -522,6 +536,52 @@ __device__ __forceinline__ void for_each_ge(const uint32_t (&v)[32], float thr, 
     if (__uint_as_float(v[31]) >= thr) f(31);
 }
 
+// ---------------------------------------------------------------------------
+// Hit handling of the collect passes.  A thread's candidate list lives in global memory (3 GB per batch: it does
+// not stay in L2), and a 4-byte store into a sector that is not resident makes L2 fetch the sector from DRAM first
+// (round 1: 6.1 GB of such reads per launch).  So indices are staged eight at a time in shared memory
+// ([slot][lane]: conflict-free) and leave as ONE whole 32-byte sector.  The rare path is compact on purpose: which
+// columns pass goes into a bit mask first (the pruned tree walk of for_each_ge), the store sequence exists once.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void flush_sector(int32_t *dst, const uint32_t *stg) {
+    const uint4 lo4 = make_uint4(stg[0], stg[32], stg[64], stg[96]);
+    const uint4 hi4 = make_uint4(stg[128], stg[160], stg[192], stg[224]);
+    reinterpret_cast<uint4 *>(dst)[0] = lo4;
+    reinterpret_cast<uint4 *>(dst)[1] = hi4;
+}
+// x0 / x1: two 32-column chunks whose first columns are domains col and col + 32; ma / mb their maxima
+#ifndef FWAV_HITS_MASK
+#define FWAV_HITS_MASK 0
+#endif
+__device__ __forceinline__ void collect_hits(const uint32_t (&x0)[32], const uint32_t (&x1)[32], float ma, float mb, float tau,
+                                             int col, int32_t *list, int room, int &cnt, uint32_t *stg) {
+    auto push = [&](int id) {
+        stg[(cnt & 7) * 32] = (uint32_t)id;
+        if ((cnt & 7) == 7 && cnt < room) flush_sector(list + (cnt - 7), stg);
+        ++cnt;
+    };
+#if FWAV_HITS_MASK
+    // which columns pass goes into a bit mask first: the store sequence exists once (ptxas turns the walk into
+    // ~2.5 predicated instructions per column)
+    unsigned long long mask = 0ull;
+    if (ma >= tau) for_each_ge(x0, tau, [&](int j) { mask |= 1ull << j; });
+    if (mb >= tau) for_each_ge(x1, tau, [&](int j) { mask |= 1ull << (32 + j); });
+    while (mask) {
+        push(col + __ffsll((long long)mask) - 1);
+        mask &= mask - 1;
+    }
+#else
+    // the pruned walk with the (short) staging sequence at every leaf: more code, fewer instructions executed
+    if (ma >= tau) for_each_ge(x0, tau, [&](int j) { push(col + j); });
+    if (mb >= tau) for_each_ge(x1, tau, [&](int j) { push(col + 32 + j); });
+#endif
+}
+__device__ __forceinline__ void collect_pair(const uint32_t (&x0)[32], const uint32_t (&x1)[32], float tau, int col,
+                                             int32_t *list, int room, int &cnt, uint32_t *stg) {
+    const float ma = chunk_max(x0), mb = chunk_max(x1);
+    if (fmaxf(ma, mb) >= tau) collect_hits(x0, x1, ma, mb, tau, col, list, room, cnt, stg);
+}
+
 // One kernel skeleton, three epilogues:
 //   MODE_LISTS    exact threshold top-K with sorted per-row lists in shared memory (any table; the
 //                 fallback of the fast path below and the path for small tables);
@@ -753,6 +813,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         for (int i = 0; i < kThetaPart; ++i) t8[i] = live ? -INFINITY : INFINITY;
         int cnt = 0;                                                // COLLECT
         int32_t *cbuf = nullptr;
+        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kOffMode) + warp * 256 + lane;    // COLLECT: slot k at stg[32 * k]
         if (MODE == MODE_COLLECT) {
             tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;  // +inf for pruned rows (written by pass 1)
             cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + half) * (long long)a.cap;
@@ -789,55 +850,29 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
             }
         } else if (kAlt && !(dbg & 8)) {
+            // (kAlt is MODE_COLLECT with HI only)  One tcgen05.ld x64 per round, both chunk maxima first (two
+            // independent trees), one compare for the pair; hits go through the staged-sector path (collect_pair).
             uint32_t x0[32], x1[32];
             int it = 0;
-            // one 32-column chunk with its maximum m: THETA keeps the group's best scores, COLLECT appends indices
-            auto look = [&](const uint32_t (&x)[32], float m, int col) {
-                if (MODE == MODE_THETA) {
-                    if (it < kThetaWarm / 2) {
-                        if (m > t8[kThetaPart - 1]) insert_desc(t8, m);      // warm-up: chunk maxima only (see below)
-                    } else if (m > t8[kThetaPart - 1]) {
-                        for_each_ge(x, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
-                            const float v = __uint_as_float(x[j]);
-                            if (v > t8[kThetaPart - 1]) insert_desc(t8, v);
-                        });
-                    }
-                } else if (m >= tau) {
-                    for_each_ge(x, tau, [&](int j) {
-                        if (cnt < a.cap) cbuf[cnt] = col + j;
-                        ++cnt;
-                    });
-                }
-            };
             tt = t_first + set;
             if (tt >= s_hi) tt -= n_visit;
             const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tempty + 8 * set;
             for (int t = set; t < n_visit; t += 2, ++it) {
                 mbar_wait_hot(bar_f, (uint32_t)(it & 1));
                 tc_fence_after();
-                tmem_ld32(t_lane, x0);
-                tmem_ld32(t_lane + 32, x1);
+                tmem_ld64(t_lane, x0, x1);
                 tmem_wait_ld2(x0, x1);
                 const int col0 = tt * kDStage + colhalf * 128;
                 tt += 2;
                 if (tt >= s_hi) tt -= n_visit;
-                {
-                    const float ma = chunk_max(x0), mb = chunk_max(x1);
-                    look(x0, ma, col0);
-                    look(x1, mb, col0 + 32);
-                }
-                tmem_ld32(t_lane + 64, x0);
-                tmem_ld32(t_lane + 96, x1);
+                collect_pair(x0, x1, tau, col0, cbuf, a.cap, cnt, stg);
+                tmem_ld64(t_lane + 64, x0, x1);
                 tmem_wait_ld2(x0, x1);
                 // the warp's share of the buffer has been read: hand it back
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (CG == 2) mbar_arrive_remote(bar_e, 0); else mbar_arrive_local(bar_e); }
-                {
-                    const float ma = chunk_max(x0), mb = chunk_max(x1);
-                    look(x0, ma, col0 + 64);
-                    look(x1, mb, col0 + 96);
-                }
+                collect_pair(x0, x1, tau, col0 + 64, cbuf, a.cap, cnt, stg);
             }
         } else if (!(dbg & 8)) {
             // Streaming epilogue: 64 columns per warp and stage, four warps per scheduler interleave their chains.
@@ -879,21 +914,13 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                                 if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
                             });
                     }
-                } else {
-                    if (ma >= tau)
-                        for_each_ge(x0, tau, [&](int j) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + j;
-                            ++cnt;
-                        });
-                    if (mb >= tau)
-                        for_each_ge(x1, tau, [&](int j) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + 32 + j;
-                            ++cnt;
-                        });
+                } else if (fmaxf(ma, mb) >= tau) {
+                    collect_hits(x0, x1, ma, mb, tau, col0, cbuf, a.cap, cnt, stg);
                 }
             }
         }
         if (MODE == MODE_COLLECT) {
+            if ((cnt & 7) && cnt < a.cap) flush_sector(cbuf + (cnt & ~7), stg);      // the last, partial sector
             if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
         } else if (MODE == MODE_THETA) {
             // theta of a row = kTheta-th largest sampled score over the four column groups.  A group keeps
@@ -1049,19 +1076,6 @@ __host__ __device__ constexpr int c4_regs(int epi, int iss) { return epi == 16 ?
 constexpr uint32_t kC4OffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
 __host__ __device__ constexpr uint32_t c4_smem(int epi) { return kC4OffStage + (uint32_t)epi * 8 * 32 * 4; }
 
-// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : FWAV_R32(v), FWAV_R32(w)
-        : "r"(taddr)
-        : "memory");
-}
-
 template <int EPI, int ISS>
 __global__ void __maxnreg__(c4_regs(EPI, ISS)) collect4_kernel(const ScanArgs a) {
     constexpr int kThreads = c4_threads(EPI, ISS);
@@ -1154,28 +1168,8 @@ __global__ void __maxnreg__(c4_regs(EPI, ISS)) collect4_kernel(const ScanArgs a)
         uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kC4OffStage) + warp * 256 + lane;    // slot k: stg[32 * k]
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(EPI == 16 ? colhalf * 64 : 0);
         int cnt = 0;
-        // eight staged indices -> one 32-byte sector of the list
-        auto flush = [&](int at) {
-            const uint4 lo4 = make_uint4(stg[0], stg[32], stg[64], stg[96]);
-            const uint4 hi4 = make_uint4(stg[128], stg[160], stg[192], stg[224]);
-            uint4 *dst = reinterpret_cast<uint4 *>(list + at);
-            dst[0] = lo4;
-            dst[1] = hi4;
-        };
-        // one pair of 32-column chunks: both maxima first (two independent trees), one compare for the pair
         auto look2 = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32], int col) {
-            const float m0 = chunk_max(x0), m1 = chunk_max(x1);
-            if (fmaxf(m0, m1) >= tau) {
-                unsigned long long mask = 0ull;
-                if (m0 >= tau) for_each_ge(x0, tau, [&](int j) { mask |= 1ull << j; });
-                if (m1 >= tau) for_each_ge(x1, tau, [&](int j) { mask |= 1ull << (32 + j); });
-                while (mask) {
-                    stg[(cnt & 7) * 32] = (uint32_t)(col + __ffsll((long long)mask) - 1);
-                    if ((cnt & 7) == 7 && cnt < room) flush(cnt - 7);
-                    ++cnt;
-                    mask &= mask - 1;
-                }
-            }
+            collect_pair(x0, x1, tau, col, list, room, cnt, stg);
         };
         const int n_own = (n_visit - set + 1) / 2;               // tiles set, set + 2, ... below n_visit
         int tt = t_first + set;
@@ -1229,7 +1223,7 @@ __global__ void __maxnreg__(c4_regs(EPI, ISS)) collect4_kernel(const ScanArgs a)
                 }
             }
         }
-        if ((cnt & 7) && cnt < room) flush(cnt & ~7);            // the last, partial sector (the count says how much of it is valid)
+        if ((cnt & 7) && cnt < room) flush_sector(list + (cnt & ~7), stg);   // the last, partial sector (the count says how much of it is valid)
         if (q < n_q) {
             int *cc = a.ccount + (q * a.n_split + split) * 4 + part0;
             if (EPI == 16) {

@@ -16,7 +16,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfwav_b200.so")
+LIB_PATH = os.environ.get("FWAV_LIB") or os.path.join(_HERE, "libfwav_b200.so")    # FWAV_LIB: experiment builds
 
 SEARCH_AUTO, SEARCH_FFMA, SEARCH_UMMA = 0, 1, 2
 
@@ -54,6 +54,9 @@ SIGNATURES = [
                               C.POINTER(C.c_int), C.POINTER(C.c_float), c_ptr]),
     ("fwav_decode_iter", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int,
                                    C.c_double, C.c_double, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_decode_iter_gated", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int,
+                                         C.c_double, C.c_double, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    ("fwav_decode_converge", C.c_int, [c_ctx, c_ptr, C.c_int, C.c_double, c_ptr, c_ptr]),
     ("fwav_compress_device", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, i64, C.c_int, C.c_int, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -363,6 +366,15 @@ class Context:
         self._check(self.lib.fwav_decode_iter(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
                                               float(s_clip), float(s_damping), int(bool(first)), d_cur, d_next,
                                               d_sums, stream))
+
+    def decode_iter_gated(self, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size, s_clip, s_damping,
+                          first, d_cur, d_next, d_sums, d_state, stream=None):
+        self._check(self.lib.fwav_decode_iter_gated(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
+                                                    float(s_clip), float(s_damping), int(bool(first)), d_cur, d_next,
+                                                    d_sums, d_state, stream))
+
+    def decode_converge(self, d_sums_all, n_parts, eps, d_state, stream=None):
+        self._check(self.lib.fwav_decode_converge(self.h, d_sums_all, int(n_parts), float(eps), d_state, stream))
 
     def compress_device(self, d_signal, n, d_ranges, n_r, query_offset, tile_size, emb_dim, top_k,
                         energy_thresh, fast_mode, query_mode, build, d_domains, d_emb,

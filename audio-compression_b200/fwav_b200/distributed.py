@@ -22,7 +22,9 @@ runs on the CUDA library (CudaEngine, below) and, in the CPU tests, on a stand-i
 built from the oracle:
     build_tables(signal, tile) -> (domains, embs)
     match_slice(ranges, lo, hi, domains, embs, ...) -> (idx, s, o, err, sym) tensors
-    decode_iter(domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt) -> sums(2,) f64
+    match_slice(ranges, lo, hi, domains, embs, ..., out=packed (5, cap) int32)   rows idx | s | o | err | sym bytes
+    new_state() / decode_iter(..., first, cur, nxt, state) -> sums(2,) f64 / converge(all_sums, parts, eps, state) /
+    read_state(state) -> (iterations run, last delta): the decode loop with its convergence decision on the device
     empty(shape, dtype) / from_numpy(...) for allocation on the engine's device
 """
 from __future__ import annotations
@@ -51,8 +53,14 @@ def _dist():
 
 
 def compress_sharded(engine, signal, ranges, tile_size, emb_dim=16, top_k=32, energy_thresh=1e-4,
-                     fast_mode=True, query_mode=0, broadcast_tables=True):
-    """Returns (idx, s, o, sym, err, domains) as engine tensors on every rank."""
+                     fast_mode=True, query_mode=0, broadcast_tables=False):
+    """Returns (idx, s, o, sym, err, domains) as engine tensors on every rank.
+
+    Tables: every rank builds the domain table and its embeddings from the (replicated) signal itself -- the
+    kernels are deterministic, so the tables are bit-identical, and 0.2 ms of HBM-bound work beats broadcasting
+    254 MB (0.85 ms measured at config 2).  `broadcast_tables=True` keeps the north star's literal form (rank 0
+    builds, NCCL broadcasts).  Matches: ONE all-gather of a packed (5, cap) int32 block per rank
+    (idx | s | o | err | sym bytes), written in place by the match kernel."""
     import torch
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -70,35 +78,32 @@ def compress_sharded(engine, signal, ranges, tile_size, emb_dim=16, top_k=32, en
         domains, embs = engine.build_tables(signal, tile_size, emb_dim)
     if query_mode == 0 and n_r > domains.shape[0]:
         raise ValueError("mmap length is greater than file size")       # fractal.py:1190
-    part = engine.match_slice(ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh,
-                              fast_mode, query_mode)
-    if world == 1:
-        idx, s, o, err, sym = part
-        return idx, s, o, sym, err, domains
-    cap = max(b - a for a, b in bounds)
-    packed = engine.empty((4, cap), torch.int32)
+    cap = max(max(b - a for a, b in bounds), 1)
+    cap = -(-cap // 4) * 4                       # the sym row is read back as bytes of whole int32 words
+    packed = engine.empty((5, cap), torch.int32)
     packed.zero_()
-    for row, t in enumerate(part[:4]):
-        packed[row, :hi - lo] = t.view(torch.int32)
-    sym = engine.empty((cap,), torch.uint8)
-    sym.zero_()
-    sym[:hi - lo] = part[4]
-    # flat buffers: accepted by both the NCCL and the gloo all-gather
-    g32 = engine.empty((world * 4 * cap,), torch.int32)
-    gsym = engine.empty((world * cap,), torch.uint8)
-    dist.all_gather_into_tensor(g32, packed.view(-1))
-    dist.all_gather_into_tensor(gsym, sym)
-    g32, gsym = g32.view(world, 4, cap), gsym.view(world, cap)
-    cols = [torch.cat([g32[r, k, :b - a] for r, (a, b) in enumerate(bounds)]) for k in range(4)]
-    sym_all = torch.cat([gsym[r, :b - a] for r, (a, b) in enumerate(bounds)])
+    engine.match_slice(ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode,
+                       query_mode, out=packed)
+    if world == 1:
+        g = packed.view(1, 5, cap)
+    else:
+        g = engine.empty((world * 5 * cap,), torch.int32)     # flat: accepted by both the NCCL and the gloo all-gather
+        dist.all_gather_into_tensor(g, packed.view(-1))
+        g = g.view(world, 5, cap)
+    cols = [torch.cat([g[r, k, :b - a] for r, (a, b) in enumerate(bounds)]) for k in range(4)]
+    sym_all = torch.cat([g[r, 4].view(torch.uint8)[:b - a] for r, (a, b) in enumerate(bounds)])
     return (cols[0], cols[1].view(torch.float32), cols[2].view(torch.float32), sym_all,
             cols[3].view(torch.float32), domains)
 
 
 def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, convergence_eps=1e-3,
                    s_clip=16.0, s_damping=0.0, gather_every_iteration=True):
-    """Every rank passes the FULL match arrays; returns (recon tensor of
-    n_ranges*range_size on every rank, iterations run, last delta)."""
+    """Every rank passes the FULL match arrays; returns (recon tensor of n_ranges*range_size on every rank,
+    iterations run, last delta).
+
+    No host read-back inside the loop: per iteration the ranks all-gather their two float64 sums, a one-thread
+    kernel adds them in rank order and takes the convergence decision into a device-side state, and the iteration
+    kernels that follow a `done` return at once.  The state is read once, after the last launch."""
     import torch
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -107,36 +112,29 @@ def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, co
     bounds = shard_bounds(n_r, world)
     lo, hi = bounds[rank]
     cap = max(b - a for a, b in bounds)
-    cur = engine.empty((cap * N,), torch.float32)
-    nxt = engine.empty((cap * N,), torch.float32)
-    cur.zero_()
-    nxt.zero_()
+    bufs = [engine.empty((cap * N,), torch.float32), engine.empty((cap * N,), torch.float32)]
+    for b in bufs:
+        b.zero_()
     full = engine.empty((world * cap * N,), torch.float32) if world > 1 else None
     all_sums = engine.empty((world * 2,), torch.float64)
-    it_run, delta = 0, 0.0
+    state = engine.new_state()
     for it in range(iterations):
+        # iteration `it` reads bufs[it & 1] and writes bufs[(it + 1) & 1]
         sums = engine.decode_iter(domains, idx[lo:hi], s[lo:hi], o[lo:hi], sym[lo:hi], N, s_clip, s_damping,
-                                  it == 0, cur, nxt)
+                                  it == 0, bufs[it & 1], bufs[(it + 1) & 1], state)
         if world > 1:
             dist.all_gather_into_tensor(all_sums, sums)
-            if gather_every_iteration:
-                dist.all_gather_into_tensor(full, nxt)
         else:
             all_sums.copy_(sums)
-        host = all_sums.cpu().numpy().reshape(world, 2)
-        dsq = csq = 0.0
-        for r in range(world):                      # rank order: bit-stable for a given world size
-            dsq += float(host[r, 0])
-            csq += float(host[r, 1])
-        delta = delta_from_sums(dsq, csq)
-        cur, nxt = nxt, cur
-        it_run = it + 1
-        if delta < convergence_eps:
-            break
+        engine.converge(all_sums, world, convergence_eps, state)        # rank order: bit-stable for a given world size
+        if world > 1 and gather_every_iteration:
+            dist.all_gather_into_tensor(full, bufs[(it + 1) & 1])
+    it_run, delta = engine.read_state(state)                            # the one synchronisation of the decode
+    cur = bufs[it_run & 1]
     if world == 1:
         return cur[:n_r * N], it_run, delta
-    if not gather_every_iteration or it_run == 0:
-        dist.all_gather_into_tensor(full, cur)
+    if not gather_every_iteration or it_run < iterations or it_run == 0:
+        dist.all_gather_into_tensor(full, cur)       # converged early: the gathers after it carried the stale buffer
     full = full.view(world, cap * N)
     out = torch.cat([full[r, :(b - a) * N] for r, (a, b) in enumerate(bounds)])
     return out, it_run, delta
@@ -180,13 +178,11 @@ class CudaEngine:
         return domains, embs
 
     def match_slice(self, ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode,
-                    query_mode):
+                    query_mode, out):
+        """Matches of ranges [lo, hi) into the packed block `out` (5, cap) int32: the kernel writes the rows."""
         t = self.torch
         N = ranges.shape[1]
         cnt = hi - lo
-        idx = self.empty((cnt,), t.int32)
-        s, o, err = (self.empty((cnt,), t.float32) for _ in range(3))
-        sym = self.empty((cnt,), t.uint8)
         if cnt:
             rp = ranges.data_ptr() + lo * N * 4
             act = self.empty((cnt,), t.uint8)
@@ -202,12 +198,27 @@ class CudaEngine:
             self.ctx.topk(qp, cnt, embs.data_ptr(), embs.shape[0], emb_dim, top_k, act.data_ptr(), cand.data_ptr(),
                           None, st)
             self.ctx.affine_match(rp, cnt, N, domains.data_ptr(), domains.shape[0], cand.data_ptr(), top_k, 16.0,
-                                  idx.data_ptr(), s.data_ptr(), o.data_ptr(), sym.data_ptr(), err.data_ptr(), st)
-        return idx, s, o, err, sym
+                                  out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[4].data_ptr(),
+                                  out[3].data_ptr(), st)
+            self._keep = (act, cand)             # alive until the stream has consumed them
+        return out
 
-    def decode_iter(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt):
-        sums = self.empty((2,), self.torch.float64)
-        self.ctx.decode_iter(domains.data_ptr(), domains.shape[0], idx.data_ptr(), s.data_ptr(), o.data_ptr(),
-                             sym.data_ptr(), idx.shape[0], N, s_clip, s_damping, first, cur.data_ptr(),
-                             nxt.data_ptr(), sums.data_ptr(), self._stream())
-        return sums
+    def new_state(self):
+        return self.torch.zeros(4, dtype=self.torch.int32, device=self.device)      # fwav_decode_state
+
+    def decode_iter(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt, state):
+        if self._sums is None:
+            self._sums = self.empty((2,), self.torch.float64)
+        self.ctx.decode_iter_gated(domains.data_ptr(), domains.shape[0], idx.data_ptr(), s.data_ptr(), o.data_ptr(),
+                                   sym.data_ptr(), idx.shape[0], N, s_clip, s_damping, first, cur.data_ptr(),
+                                   nxt.data_ptr(), self._sums.data_ptr(), state.data_ptr(), self._stream())
+        return self._sums
+
+    def converge(self, all_sums, parts, eps, state):
+        self.ctx.decode_converge(all_sums.data_ptr(), parts, eps, state.data_ptr(), self._stream())
+
+    def read_state(self, state):
+        h = state.cpu()
+        if int(h[3]):
+            raise IndexError("index out of bounds: a match points past the domain table")
+        return int(h[0]), float(h[2:3].view(self.torch.float32)[0])

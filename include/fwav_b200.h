@@ -136,6 +136,28 @@ int fwav_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
                      int64_t n_ranges, int range_size, double s_clip, double s_damping, int first,
                      const float *d_cur, float *d_next, double *d_sums, void *stream);
 
+/* The same with the convergence decision on the device (no host read-back per iteration).  d_state points at a
+ * ZEROED fwav_decode_state in device memory that the caller keeps for the whole decode:
+ *   fwav_decode_iter_gated   returns at once (d_next untouched) when d_state->done is set;
+ *   fwav_decode_converge     adds the n_parts pairs of sums in d_sums_all ([part][2] float64, e.g. the all-gathered
+ *                            d_sums of every rank) in index order, computes delta as fractal.py:1460-1461 does,
+ *                            counts the iteration and sets `done` when delta < convergence_eps (:1465).
+ * After the last launch the caller reads the state once: iters_run iterations ran, and iteration `it` wrote the
+ * buffer that was its d_next. */
+typedef struct fwav_decode_state {
+    int32_t iters_run;
+    int32_t done;
+    float delta;
+    int32_t bad_index;   /* a match pointed past the domain table (it was decoded as a sentinel) */
+} fwav_decode_state;
+int fwav_decode_iter_gated(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
+                           const int32_t *d_idx, const float *d_s, const float *d_o, const uint8_t *d_sym,
+                           int64_t n_ranges, int range_size, double s_clip, double s_damping, int first,
+                           const float *d_cur, float *d_next, double *d_sums,
+                           fwav_decode_state *d_state, void *stream);
+int fwav_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double convergence_eps,
+                         fwav_decode_state *d_state, void *stream);
+
 /* Device pipeline A1..A7 on resident inputs: replaces the process/queue
  * pipeline of compress_audio (fractal.py:1114-1245) between "ranges framed"
  * and "matches collected".  d_signal is the raw signal (domains are built

@@ -39,15 +39,39 @@ class OracleEngine:
             return out
         return torch.from_numpy(dom), torch.from_numpy(emb)
 
-    def match_slice(self, ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode, query_mode):
+    def match_slice(self, ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode, query_mode,
+                    out):
         r, e, d = ranges.numpy(), embs.numpy(), domains.numpy()
         q = e if query_mode == 0 else O.embed_rows(r, emb_dim)
         ids = np.arange(lo, hi)
         cand = O.candidates_for_ranges(r, q, e, top_k, energy_thresh, fast_mode, which=ids)
         m = O.affine_match(r[ids], cand, d)
-        return tuple(torch.from_numpy(m[k]) for k in ("idx", "s", "o", "err", "sym"))
+        o = out.numpy()                                   # packed rows, as the CUDA kernel writes them
+        for row, k in enumerate(("idx", "s", "o", "err")):
+            o[row, :hi - lo] = m[k].view(np.int32)
+        o[4].view(np.uint8)[:hi - lo] = m["sym"]
+        return out
 
-    def decode_iter(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt):
+    def new_state(self):
+        return dict(iters=0, done=False, delta=0.0)
+
+    def converge(self, all_sums, parts, eps, state):
+        if state["done"]:
+            return
+        h = all_sums.numpy().reshape(parts, 2)
+        dsq = csq = 0.0
+        for r in range(parts):                            # rank order
+            dsq += float(h[r, 0]); csq += float(h[r, 1])
+        state["delta"] = D.delta_from_sums(dsq, csq)
+        state["iters"] += 1
+        state["done"] = state["delta"] < eps
+
+    def read_state(self, state):
+        return state["iters"], state["delta"]
+
+    def decode_iter(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt, state):
+        if state["done"]:
+            return torch.zeros(2, dtype=torch.float64)
         n = idx.shape[0]
         c = np.zeros(n * N, np.float32) if first else cur.numpy()[:n * N].copy()
         # one oracle iteration from the given state: replay its loop body
