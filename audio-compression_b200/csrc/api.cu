@@ -223,6 +223,13 @@ int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl) {
     return FWAV_OK;
 }
 
+int fwav_ctx_set_search_range_size(fwav_ctx *ctx, int range_size) {
+    if (!ctx) return FWAV_ERR_INVALID;
+    FWAV_REQUIRE(ctx, range_size >= 0 && range_size <= fwm::kMaxRangeSize, "range_size %d out of range", range_size);
+    ctx->search_range_size = range_size;
+    return FWAV_OK;
+}
+
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx) { return ctx ? ctx->umma_fallback_queries : 0; }
 int fwav_ctx_search_timings(fwav_ctx *ctx, float ms[5]) {
@@ -401,8 +408,11 @@ int fwav_compress_device(fwav_ctx *ctx, const float *d_signal, int64_t n_samples
         if ((rc = fwav_launch_embed(ctx, d_ranges, n_ranges, N, emb_dim, d_qe, st))) return rc;
         d_q = d_qe;
     }
-    if ((rc = topk_dispatch(ctx, d_q, n_ranges, d_emb, n_dom, emb_dim, top_k, d_active, d_cand, nullptr, st)))
-        return rc;
+    const int hint_before = ctx->search_range_size;
+    ctx->search_range_size = N;          // both tables were embedded for this geometry (queries: rows of d_emb, or the ranges)
+    rc = topk_dispatch(ctx, d_q, n_ranges, d_emb, n_dom, emb_dim, top_k, d_active, d_cand, nullptr, st);
+    ctx->search_range_size = hint_before;
+    if (rc) return rc;
     return fwav_launch_affine(ctx, d_ranges, n_ranges, N, d_domains, n_dom, d_cand, top_k, 16.0, d_idx, d_s,
                               d_o, d_sym, d_err, st);
 }

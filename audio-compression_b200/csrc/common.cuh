@@ -30,6 +30,11 @@ struct fwav_ctx {
     bool search_fast_path = false;
     bool search_hi_only = false;          // last collect pass filtered with the hi*hi term alone
 
+    // range_size the embedding tables of the coming searches were built for (0: unknown).  Set by the pipeline
+    // entry points around their own search, or by fwav_ctx_set_search_range_size; tells the tensor-core search
+    // which embedding dimensions can be non-zero at all (fractal.py:154-208) without a device round trip.
+    int search_range_size = 0;
+
     // embedding matrices cached per (N, half)
     int emb_N = 0, emb_half = 0;
     double *d_tonal = nullptr, *d_transient = nullptr, *d_w = nullptr;

@@ -90,8 +90,7 @@ constexpr int kThetaWarm = 24;         // first stages of pass 1 that only look 
 constexpr uint32_t kOffScratch = kOffMode + kQTile * 2 * kCap * 8;
 // MODE_THETA: [row][3][kThetaPart] scores of column groups 1..3 for the final merge
 __host__ __device__ constexpr uint32_t mode_bytes(int mode) {
-    // MODE_COLLECT: [warp][slot 0..7][lane] candidate indices staged for whole-sector stores (16 warps x 1 KB)
-    return mode == MODE_LISTS ? (kOffScratch - kOffMode) + 8 * 128 * 4 : mode == MODE_THETA ? kQTile * 3 * kThetaPart * 4 : 16 * 8 * 32 * 4;
+    return mode == MODE_LISTS ? (kOffScratch - kOffMode) + 8 * 128 * 4 : mode == MODE_THETA ? kQTile * 3 * kThetaPart * 4 : 0;
 }
 __host__ __device__ constexpr uint32_t off_ring(int mode) { return (kOffMode + mode_bytes(mode) + 1023u) & ~1023u; }
 // a stage is 256 domains: one 8 KB tile per CTA of a pair, or both tiles (16 KB) in a CTA on its own
@@ -249,19 +248,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-// 32 lanes x 64 columns of one TMEM lane quadrant -> 64 registers per thread (asynchronous)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[32], uint32_t (&w)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : FWAV_R32(v), FWAV_R32(w)
-        : "r"(taddr)
-        : "memory");
-}
-
 // wait for the loads; the registers are threaded through so no use can be scheduled above it
 __device__ __forceinline__ void tmem_wait_ld1(uint32_t (&a)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a)::"memory");
@@ -324,7 +310,7 @@ pack_f16_tiles_kernel(const float *__restrict__ src, long long n_rows, long long
 }
 
 // ---------------------------------------------------------------------------
-// EXPERIMENTAL (FWAV_UMMA_COMPACT=1; written at the end of round 1, NOT yet run on a GPU): compact split.
+// Compact split (validated on B200 in round 2: equal to the FFMA kernel on every route, tests/test_gpu_parity.py).
 // With range_size 4 (the reference's default tile_size 1024, BASELINE config 4) only 7 of the 16 embedding
 // dimensions are ever non-zero (3 tonal + 4 transient, fractal.py:154-208).  Eight live dimensions leave room for
 // the hi AND the lo part in one K = 16 operand, so the full split needs two MMAs per stage instead of three:
@@ -534,52 +520,6 @@ __device__ __forceinline__ void for_each_ge(const uint32_t (&v)[32], float thr, 
     }
     if (__uint_as_float(v[30]) >= thr) f(30);
     if (__uint_as_float(v[31]) >= thr) f(31);
-}
-
-// ---------------------------------------------------------------------------
-// Hit handling of the collect passes.  A thread's candidate list lives in global memory (3 GB per batch: it does
-// not stay in L2), and a 4-byte store into a sector that is not resident makes L2 fetch the sector from DRAM first
-// (round 1: 6.1 GB of such reads per launch).  So indices are staged eight at a time in shared memory
-// ([slot][lane]: conflict-free) and leave as ONE whole 32-byte sector.  The rare path is compact on purpose: which
-// columns pass goes into a bit mask first (the pruned tree walk of for_each_ge), the store sequence exists once.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void flush_sector(int32_t *dst, const uint32_t *stg) {
-    const uint4 lo4 = make_uint4(stg[0], stg[32], stg[64], stg[96]);
-    const uint4 hi4 = make_uint4(stg[128], stg[160], stg[192], stg[224]);
-    reinterpret_cast<uint4 *>(dst)[0] = lo4;
-    reinterpret_cast<uint4 *>(dst)[1] = hi4;
-}
-// x0 / x1: two 32-column chunks whose first columns are domains col and col + 32; ma / mb their maxima
-#ifndef FWAV_HITS_MASK
-#define FWAV_HITS_MASK 0
-#endif
-__device__ __forceinline__ void collect_hits(const uint32_t (&x0)[32], const uint32_t (&x1)[32], float ma, float mb, float tau,
-                                             int col, int32_t *list, int room, int &cnt, uint32_t *stg) {
-    auto push = [&](int id) {
-        stg[(cnt & 7) * 32] = (uint32_t)id;
-        if ((cnt & 7) == 7 && cnt < room) flush_sector(list + (cnt - 7), stg);
-        ++cnt;
-    };
-#if FWAV_HITS_MASK
-    // which columns pass goes into a bit mask first: the store sequence exists once (ptxas turns the walk into
-    // ~2.5 predicated instructions per column)
-    unsigned long long mask = 0ull;
-    if (ma >= tau) for_each_ge(x0, tau, [&](int j) { mask |= 1ull << j; });
-    if (mb >= tau) for_each_ge(x1, tau, [&](int j) { mask |= 1ull << (32 + j); });
-    while (mask) {
-        push(col + __ffsll((long long)mask) - 1);
-        mask &= mask - 1;
-    }
-#else
-    // the pruned walk with the (short) staging sequence at every leaf: more code, fewer instructions executed
-    if (ma >= tau) for_each_ge(x0, tau, [&](int j) { push(col + j); });
-    if (mb >= tau) for_each_ge(x1, tau, [&](int j) { push(col + 32 + j); });
-#endif
-}
-__device__ __forceinline__ void collect_pair(const uint32_t (&x0)[32], const uint32_t (&x1)[32], float tau, int col,
-                                             int32_t *list, int room, int &cnt, uint32_t *stg) {
-    const float ma = chunk_max(x0), mb = chunk_max(x1);
-    if (fmaxf(ma, mb) >= tau) collect_hits(x0, x1, ma, mb, tau, col, list, room, cnt, stg);
 }
 
 // One kernel skeleton, three epilogues:
@@ -813,7 +753,6 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         for (int i = 0; i < kThetaPart; ++i) t8[i] = live ? -INFINITY : INFINITY;
         int cnt = 0;                                                // COLLECT
         int32_t *cbuf = nullptr;
-        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kOffMode) + warp * 256 + lane;    // COLLECT: slot k at stg[32 * k]
         if (MODE == MODE_COLLECT) {
             tau = (q < n_q && !(dbg & 4)) ? a.theta[q] : INFINITY;  // +inf for pruned rows (written by pass 1)
             cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + half) * (long long)a.cap;
@@ -850,29 +789,55 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
             }
         } else if (kAlt && !(dbg & 8)) {
-            // (kAlt is MODE_COLLECT with HI only)  One tcgen05.ld x64 per round, both chunk maxima first (two
-            // independent trees), one compare for the pair; hits go through the staged-sector path (collect_pair).
             uint32_t x0[32], x1[32];
             int it = 0;
+            // one 32-column chunk with its maximum m: THETA keeps the group's best scores, COLLECT appends indices
+            auto look = [&](const uint32_t (&x)[32], float m, int col) {
+                if (MODE == MODE_THETA) {
+                    if (it < kThetaWarm / 2) {
+                        if (m > t8[kThetaPart - 1]) insert_desc(t8, m);      // warm-up: chunk maxima only (see below)
+                    } else if (m > t8[kThetaPart - 1]) {
+                        for_each_ge(x, nextafterf(t8[kThetaPart - 1], INFINITY), [&](int j) {
+                            const float v = __uint_as_float(x[j]);
+                            if (v > t8[kThetaPart - 1]) insert_desc(t8, v);
+                        });
+                    }
+                } else if (m >= tau) {
+                    for_each_ge(x, tau, [&](int j) {
+                        if (cnt < a.cap) cbuf[cnt] = col + j;
+                        ++cnt;
+                    });
+                }
+            };
             tt = t_first + set;
             if (tt >= s_hi) tt -= n_visit;
             const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tempty + 8 * set;
             for (int t = set; t < n_visit; t += 2, ++it) {
                 mbar_wait_hot(bar_f, (uint32_t)(it & 1));
                 tc_fence_after();
-                tmem_ld64(t_lane, x0, x1);
+                tmem_ld32(t_lane, x0);
+                tmem_ld32(t_lane + 32, x1);
                 tmem_wait_ld2(x0, x1);
                 const int col0 = tt * kDStage + colhalf * 128;
                 tt += 2;
                 if (tt >= s_hi) tt -= n_visit;
-                collect_pair(x0, x1, tau, col0, cbuf, a.cap, cnt, stg);
-                tmem_ld64(t_lane + 64, x0, x1);
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0);
+                    look(x1, mb, col0 + 32);
+                }
+                tmem_ld32(t_lane + 64, x0);
+                tmem_ld32(t_lane + 96, x1);
                 tmem_wait_ld2(x0, x1);
                 // the warp's share of the buffer has been read: hand it back
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (CG == 2) mbar_arrive_remote(bar_e, 0); else mbar_arrive_local(bar_e); }
-                collect_pair(x0, x1, tau, col0 + 64, cbuf, a.cap, cnt, stg);
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0 + 64);
+                    look(x1, mb, col0 + 96);
+                }
             }
         } else if (!(dbg & 8)) {
             // Streaming epilogue: 64 columns per warp and stage, four warps per scheduler interleave their chains.
@@ -914,13 +879,21 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                                 if (x > t8[kThetaPart - 1]) insert_desc(t8, x);
                             });
                     }
-                } else if (fmaxf(ma, mb) >= tau) {
-                    collect_hits(x0, x1, ma, mb, tau, col0, cbuf, a.cap, cnt, stg);
+                } else {
+                    if (ma >= tau)
+                        for_each_ge(x0, tau, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + j;
+                            ++cnt;
+                        });
+                    if (mb >= tau)
+                        for_each_ge(x1, tau, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + 32 + j;
+                            ++cnt;
+                        });
                 }
             }
         }
         if (MODE == MODE_COLLECT) {
-            if ((cnt & 7) && cnt < a.cap) flush_sector(cbuf + (cnt & ~7), stg);      // the last, partial sector
             if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
         } else if (MODE == MODE_THETA) {
             // theta of a row = kTheta-th largest sampled score over the four column groups.  A group keeps
@@ -1034,215 +1007,6 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 // that fail (too few candidates, buffer overflow, boundary within the slack) go
 // on the list for the exact MODE_LISTS kernel.
 // ---------------------------------------------------------------------------
-constexpr int kQuadRing = 16;                                  // 128-domain tiles in flight (8 KB each: hi | lo)
-constexpr uint32_t kQuadOffBars = kTileBytes;                  // after the query tile
-constexpr uint32_t kQuadOffRing = kTileBytes + 1024;           // 1024-aligned
-constexpr uint32_t kQuadIdesc = (1u << 4) | ((uint32_t)(kDTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);   // D=F32, A=B=F16, N=128, M=128
-
-__device__ __forceinline__ void umma_f16_m128n128(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kQuadIdesc), "r"(accumulate)
-        : "memory");
-}
-
-// ---------------------------------------------------------------------------
-// collect4_kernel: the hi*hi-only collect pass with FOUR 128-column accumulator buffers (round 2).
-//
-// What bounded scan_kernel<MODE_COLLECT, true, 1>: TMEM has room for two 256-column accumulators
-// only, a buffer is held for two rounds of load + reduce before it goes back, and ONE issue of a tcgen05.mma is a
-// serial chain (two mbarrier waits, the instruction -- which blocks its thread until the tensor pipe takes it --
-// two commits) several hundred cycles long.  Here a tile is 128 domains (M128 N128 K16), TMEM holds four
-// accumulators, up to four threads issue (ISS), a set of epilogue warps owns the tiles t = s (mod 2) and finds its
-// next accumulator ready when it comes back.  Two epilogue layouts:
-//   EPI = 16 ("thin"): warp = (TMEM lane quadrant, set, column half); one tcgen05.ld x64 per own tile, the buffer
-//                      goes back right after it, 96 registers, four warps per scheduler;
-//   EPI = 8  ("fat"):  warp = (lane quadrant, set) reads all 128 columns of an own tile; the loads are software-
-//                      pipelined across tiles (columns 0-63 of the next own tile travel while columns 64-127 of this
-//                      one are reduced), 128 data registers, two warps per scheduler.
-// Hits (a score >= the row's threshold) are staged eight at a time in shared memory and leave as whole 32-byte
-// sectors, so L2 never has to fetch a sector from DRAM to merge a 4-byte store into it (round 1: 6.1 GB of such
-// reads per launch).  The rare path is compact on purpose (which columns pass goes into a bit mask first, the store
-// sequence exists once per pair of chunks): the loop body stays within the instruction cache.
-// Candidate lists: EPI = 16 -> part (set + 2 * column half) of the row's buffer, as scan_kernel; EPI = 8 -> parts
-// (2 * set, 2 * set + 1) laid end to end.  finalize_kernel reads the parts as before.
-// ---------------------------------------------------------------------------
-__host__ __device__ constexpr int c4_threads(int epi, int iss) { return (epi + 1 + iss) * 32; }
-// registers are split four ways (one file of 16 K per scheduler): 16 + 1 + 3 = 20 warps of 96 registers are five
-// per scheduler, 8 + 1 + 3 = 12 warps of 168 are three; a fourth issuer warp does not fit either layout
-__host__ __device__ constexpr int c4_regs(int epi, int iss) { return epi == 16 ? 96 : 168; }
-constexpr uint32_t kC4OffStage = kQuadOffRing + kQuadRing * kTileBytes;       // [warp][slot 0..7][lane] staged indices
-__host__ __device__ constexpr uint32_t c4_smem(int epi) { return kC4OffStage + (uint32_t)epi * 8 * 32 * 4; }
-
-template <int EPI, int ISS>
-__global__ void __maxnreg__(c4_regs(EPI, ISS)) collect4_kernel(const ScanArgs a) {
-    constexpr int kThreads = c4_threads(EPI, ISS);
-    constexpr uint32_t kOpBytes = kPartBytes;                    // the hi parts alone
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_q = a.n_q;
-    const uint8_t *__restrict__ active = a.active;
-    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
-    const long long q_base = (long long)group_id * kQTile;
-    const uint32_t bars = smem_u32(smem + kQuadOffBars);
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQuadRing, bar_tfull = bars + 16 * kQuadRing,
-                   bar_tempty = bar_tfull + 32, bar_a = bar_tempty + 32;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQuadOffBars + 16 * kQuadRing + 80);
-
-    {   // energy-pruned stretch: nothing to scan
-        int any = 0;
-        for (int i = threadIdx.x; i < kQTile; i += kThreads) {
-            const long long q = q_base + i;
-            if (q < n_q && (!active || active[q])) any = 1;
-        }
-        if (!__syncthreads_or(any)) {
-            for (int i = threadIdx.x; i < kQTile; i += kThreads) {
-                const long long q = q_base + i;
-                if (q < n_q)
-                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
-            }
-            return;
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kQuadRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, EPI / 2); }
-        mbar_init(bar_a, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == EPI) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // this CTA's share of the table, in 128-domain tiles; the scan starts at the CTA's own rows and wraps around
-    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
-    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;
-    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
-
-    if (warp == EPI) {
-        // ===== producer: one bulk copy per tile (the hi part is the first 4 KB of a packed tile) =====
-        if (lane == 0) {
-            mbar_expect_tx(bar_a, kOpBytes);
-            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kOpBytes, bar_a);
-            int tt = t_first;
-            for (int t = 0; t < n_visit; ++t) {
-                const int s = t & (kQuadRing - 1);
-                mbar_wait(bar_empty + 8 * s, (uint32_t)(((t / kQuadRing) & 1) ^ 1));
-                mbar_expect_tx(bar_full + 8 * s, kOpBytes);
-                bulk_g2s(smem_u32(smem + kQuadOffRing + s * kTileBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kOpBytes,
-                         bar_full + 8 * s);
-                if (++tt == t_hi) tt = t_lo;
-            }
-        }
-    } else if (warp > EPI) {
-        // ===== MMA issuers: thread i owns the tiles t = i (mod ISS); tile t goes into buffer t & 3 =====
-        if (lane == 0) {
-            mbar_wait(bar_a, 0);
-            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
-            for (int t = warp - (EPI + 1); t < n_visit; t += ISS) {
-                const int s = t & (kQuadRing - 1), buf = t & 3;
-                const uint64_t db_hi = smem_desc(smem_u32(smem + kQuadOffRing + s * kTileBytes));
-                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQuadRing) & 1));
-                mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((t >> 2) & 1) ^ 1));
-                tc_fence_after();
-                umma_f16_m128n128(tmem_base + (uint32_t)(buf * kDTile), da_hi, db_hi, 0);
-                umma_commit<1>(bar_tfull + 8 * buf);
-                umma_commit<1>(bar_empty + 8 * s);
-            }
-        }
-    } else {
-        // ===== epilogue: one query row per thread =====
-        const int quad = warp & 3, set = (warp >> 2) & 1, colhalf = warp >> 3;      // colhalf: EPI == 16 only
-        const long long q = q_base + quad * 32 + lane;
-        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
-        // this thread's list: EPI == 16: part set + 2 * colhalf; EPI == 8: parts 2 * set and 2 * set + 1, end to end
-        const int part0 = EPI == 16 ? set + 2 * colhalf : 2 * set;
-        const int room = EPI == 16 ? a.cap : 2 * a.cap;
-        int32_t *list = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + part0) * (long long)a.cap;
-        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kC4OffStage) + warp * 256 + lane;    // slot k: stg[32 * k]
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(EPI == 16 ? colhalf * 64 : 0);
-        int cnt = 0;
-        auto look2 = [&](const uint32_t (&x0)[32], const uint32_t (&x1)[32], int col) {
-            collect_pair(x0, x1, tau, col, list, room, cnt, stg);
-        };
-        const int n_own = (n_visit - set + 1) / 2;               // tiles set, set + 2, ... below n_visit
-        int tt = t_first + set;
-        if (tt >= t_hi) tt -= n_visit;
-        if (EPI == 16) {
-            for (int i = 0; i < n_own; ++i) {
-                const int buf = set + 2 * (i & 1);
-                uint32_t x0[32], x1[32];
-                mbar_wait(bar_tfull + 8 * buf, (uint32_t)((i >> 1) & 1));
-                tc_fence_after();
-                tmem_ld64(t_lane + (uint32_t)(buf * kDTile), x0, x1);
-                tmem_wait_ld2(x0, x1);
-                // this warp's share of the accumulator is in registers: hand it back before looking at it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
-                const int col = tt * kDTile + colhalf * 64;
-                tt += 2;
-                if (tt >= t_hi) tt -= n_visit;
-                look2(x0, x1, col);
-            }
-        } else if (n_own > 0) {
-            uint32_t p0[32], p1[32], r0[32], r1[32];             // columns 0-63 and 64-127 of the tile in hand
-            mbar_wait(bar_tfull + 8 * set, 0);
-            tc_fence_after();
-            tmem_ld64(t_lane + (uint32_t)(set * kDTile), p0, p1);
-            tmem_wait_ld2(p0, p1);
-            tmem_ld64(t_lane + (uint32_t)(set * kDTile) + 64, r0, r1);
-            for (int i = 0; i < n_own; ++i) {
-                const int buf = set + 2 * (i & 1);
-                const int col = tt * kDTile;
-                tt += 2;
-                if (tt >= t_hi) tt -= n_visit;
-                look2(p0, p1, col);
-                tmem_wait_ld2(r0, r1);
-                // the whole tile is in registers: hand the accumulator back
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(bar_tempty + 8 * buf);
-                const bool more = i + 1 < n_own;
-                const int nbuf = set + 2 * ((i + 1) & 1);
-                if (more) {
-                    mbar_wait(bar_tfull + 8 * nbuf, (uint32_t)(((i + 1) >> 1) & 1));
-                    tc_fence_after();
-                    tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile), p0, p1);
-                }
-                look2(r0, r1, col + 64);
-                if (more) {
-                    tmem_wait_ld2(p0, p1);
-                    tmem_ld64(t_lane + (uint32_t)(nbuf * kDTile) + 64, r0, r1);
-                }
-            }
-        }
-        if ((cnt & 7) && cnt < room) flush_sector(list + (cnt & ~7), stg);   // the last, partial sector (the count says how much of it is valid)
-        if (q < n_q) {
-            int *cc = a.ccount + (q * a.n_split + split) * 4 + part0;
-            if (EPI == 16) {
-                cc[0] = cnt;                                     // above cap: finalize_kernel reads it as an overflow
-            } else {
-                const int c0 = cnt < a.cap ? cnt : a.cap;
-                cc[0] = c0;
-                cc[1] = cnt - c0;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == EPI) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core score - canonical float32 score| (measured max 3.9e-7)
 // hi*hi term alone: inputs rounded to fp16 (relative 2^-11 each), sum |q_k e_k| <= |q||e| <= 2 (two unit heads):
 // 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
@@ -1503,7 +1267,6 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
-constexpr const char *kDefaultCollect = "sets"; // default layout of the hi*hi-only collect pass (see FWAV_UMMA_COLLECT)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
 inline int grid_for(const fwav_ctx *ctx, long long work) {
@@ -1518,15 +1281,6 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
     // function attributes are per device: set before every launch (a process may hold contexts on several GPUs)
     FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     scan_kernel<MODE, HI, CG, COMPACT><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
-    FWAV_LAUNCH_CHECK(ctx);
-    return FWAV_OK;
-}
-
-// the four-buffer collect pass (hi*hi-only batches; see collect4_kernel): one CTA per 128 queries and table share
-template <int EPI, int ISS>
-int launch_c4(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect4_kernel<EPI, ISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c4_smem(EPI)));
-    collect4_kernel<EPI, ISS><<<(unsigned)(groups * split), c4_threads(EPI, ISS), c4_smem(EPI), st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1597,12 +1351,20 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_Q, (size_t)q_tiles * kTileBytes, (void **)&d_qt))) return rc;
     ctx->search_slots_used = 0;
     if ((rc = mark(ctx, 0, 0, st))) return rc;
-    // EXPERIMENTAL compact split (FWAV_UMMA_COMPACT=1, see pack_compact_tiles_kernel): which dimensions are live?
+    // Compact split (see pack_compact_tiles_kernel): at most eight live embedding dimensions leave room for the hi AND
+    // the lo part in one K = 16 operand -- two MMAs per stage instead of three for the full split (range_size 4, the
+    // reference's default tile_size: 3 tonal + 4 transient dimensions; config-4 shape collect pass 1 824 -> 1 706 ms).
+    // Which dimensions can be non-zero is known without looking at the data when the caller states the range_size
+    // the tables were embedded for (the pipeline entry points do; fwav_ctx_set_search_range_size for fwav_topk);
+    // FWAV_UMMA_COMPACT=1 probes arbitrary tables on the device (one round trip), =0 switches the split off.
     LivePerm perm = {};
     bool compact = false;
     {
         const char *c_env = getenv("FWAV_UMMA_COMPACT"), *cg2_env = getenv("FWAV_UMMA_CG");
-        if (c_env && atoi(c_env) == 1 && !(cg2_env && atoi(cg2_env) == 2) && n_d >= (1 << 16)) {
+        const bool allowed = !(c_env && atoi(c_env) == 0) && !(cg2_env && atoi(cg2_env) == 2) && n_d >= (1 << 16);
+        unsigned live = 0xffffu;
+        bool known = false;
+        if (allowed && c_env && atoi(c_env) == 1) {
             unsigned *d_mask = nullptr;
             if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, 2 * sizeof(unsigned), (void **)&d_mask))) return rc;
             FWAV_CUDA(ctx, cudaMemsetAsync(d_mask, 0, 2 * sizeof(unsigned), st));
@@ -1613,16 +1375,24 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             unsigned h_mask[2] = {0, 0};
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_mask, d_mask, sizeof h_mask, cudaMemcpyDeviceToHost, st));
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
-            const unsigned live = h_mask[0] & h_mask[1];    // a dimension dead on either side adds exactly 0 to every score
-            if (__builtin_popcount(live) <= 8) {
-                compact = true;
-                for (int k = 0; k < ED; ++k)
-                    if (live >> k & 1) perm.dim[perm.n++] = k;
-            }
-            if (getenv("FWAV_UMMA_VERBOSE"))
-                fprintf(stderr, "[fwav] live embedding dimensions: table %04x, queries %04x: %s split\n", h_mask[0], h_mask[1],
-                        compact ? "compact (2 MMAs per stage)" : "plain");
+            live = h_mask[0] & h_mask[1];    // a dimension dead on either side adds exactly 0 to every score
+            known = true;
+        } else if (allowed && ctx->search_range_size > 0) {
+            // tables built by fwav_embed for this range_size: min(8, N - 1) tonal and min(8, N) transient dimensions
+            const int N = ctx->search_range_size;
+            live = 0;
+            for (int k = 0; k < ED / 2 && k < N - 1; ++k) live |= 1u << k;
+            for (int k = 0; k < ED / 2 && k < N; ++k) live |= 1u << (ED / 2 + k);
+            known = true;
         }
+        if (known && __builtin_popcount(live) <= 8) {
+            compact = true;
+            for (int k = 0; k < ED; ++k)
+                if (live >> k & 1) perm.dim[perm.n++] = k;
+        }
+        if (getenv("FWAV_UMMA_VERBOSE"))
+            fprintf(stderr, "[fwav] live embedding dimensions %04x (%s): %s split\n", live, known ? "known" : "unknown",
+                    compact ? "compact (2 MMAs per stage)" : "plain");
     }
     // row-major float32 -> packed fp16 tiles (role 0: queries, 1: domains; stride > 1: the sample table of pass 1)
     auto pack = [&](const float *src, long long rows, long long tiles, uint4 *dst, int stride, int role) -> int {
@@ -1671,10 +1441,6 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = pack(d_emb, n_d, s_stages * 2, d_es, sample_stride, 1))) return rc;
     const char *cg_env = getenv("FWAV_UMMA_CG");
     const bool single = !(cg_env && atoi(cg_env) == 2);
-    // layout of the hi*hi-only collect pass: "sets" (scan_kernel: two 256-column buffers, two epilogue sets) or
-    // collect4_kernel as "thin3" / "thin2" / "fat3" / "fat2" (epilogue layout, issuer threads); all return the same
-    const char *layout_env = getenv("FWAV_UMMA_COLLECT");
-    const char *layout = single ? (layout_env ? layout_env : kDefaultCollect) : "sets";
     long long batch_cap = kBatchQueries;
     if (const char *batch_env = getenv("FWAV_UMMA_BATCH")) {  // test knob: small batches exercise the multi-batch loop
         const long long v = atoll(batch_env);
@@ -1690,7 +1456,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
     if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
         const int v = atoi(cap_env);
-        if (v >= 16 && v <= collect_cap) collect_cap = v & ~15;    // parts stay whole 32-byte sectors, halved too
+        if (v >= 2 && v <= collect_cap) collect_cap = v & ~1;
     }
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CBUF, (size_t)batch * 4 * collect_cap * sizeof(int32_t), (void **)&d_cbuf))) return rc;
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_CNT, (size_t)batch * 4 * sizeof(int), (void **)&d_cnt))) return rc;
@@ -1784,11 +1550,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
-            if (hi_only && !strcmp(layout, "thin3")) rc = launch_c4<16, 3>(ctx, ax, g, sp, st);
-            else if (hi_only && !strcmp(layout, "thin2")) rc = launch_c4<16, 2>(ctx, ax, g, sp, st);
-            else if (hi_only && !strcmp(layout, "fat3")) rc = launch_c4<8, 3>(ctx, ax, g, sp, st);
-            else if (hi_only && !strcmp(layout, "fat2")) rc = launch_c4<8, 2>(ctx, ax, g, sp, st);
-            else if (compact && !hi_only)
+            if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
             else if (hi_only)
                 rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);

@@ -38,6 +38,7 @@ SIGNATURES = [
     ("fwav_last_error", C.c_char_p, [c_ctx]),
     ("fwav_ctx_sync", C.c_int, [c_ctx]),
     ("fwav_ctx_set_search_impl", C.c_int, [c_ctx, C.c_int]),
+    ("fwav_ctx_set_search_range_size", C.c_int, [c_ctx, C.c_int]),
     ("fwav_ctx_launch_count", i64, [c_ctx]),
     ("fwav_ctx_search_fallbacks", i64, [c_ctx]),
     ("fwav_ctx_search_timings", C.c_int, [c_ctx, C.POINTER(C.c_float)]),
@@ -222,6 +223,9 @@ class Context:
 
     def set_search_impl(self, impl):
         self._check(self.lib.fwav_ctx_set_search_impl(self.h, int(impl)))
+
+    def set_search_range_size(self, range_size):
+        self._check(self.lib.fwav_ctx_set_search_range_size(self.h, int(range_size)))
 
     def launch_count(self):
         return int(self.lib.fwav_ctx_launch_count(self.h))

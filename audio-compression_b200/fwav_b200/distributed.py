@@ -143,13 +143,13 @@ def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, co
 class CudaEngine:
     """The engine on libfwav_b200.so: torch tensors for memory, the C ABI for work."""
 
-    def __init__(self, device):
+    def __init__(self, device, ctx=None):
         import torch
         from . import _lib
         self.torch = torch
         self.lib = _lib
         self.device = torch.device("cuda", device)
-        self.ctx = _lib.Context(device)
+        self.ctx = ctx if ctx is not None else _lib.Context(device)
         self._sums = None
 
     def _stream(self):
@@ -195,8 +195,12 @@ class CudaEngine:
                 q = self.empty((cnt, emb_dim), t.float32)
                 self.ctx.embed(rp, cnt, N, emb_dim, q.data_ptr(), st)
                 qp = q.data_ptr()
-            self.ctx.topk(qp, cnt, embs.data_ptr(), embs.shape[0], emb_dim, top_k, act.data_ptr(), cand.data_ptr(),
-                          None, st)
+            self.ctx.set_search_range_size(N)        # both tables come from fwav_embed for this geometry
+            try:
+                self.ctx.topk(qp, cnt, embs.data_ptr(), embs.shape[0], emb_dim, top_k, act.data_ptr(), cand.data_ptr(),
+                              None, st)
+            finally:
+                self.ctx.set_search_range_size(0)
             self.ctx.affine_match(rp, cnt, N, domains.data_ptr(), domains.shape[0], cand.data_ptr(), top_k, 16.0,
                                   out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[4].data_ptr(),
                                   out[3].data_ptr(), st)

@@ -58,6 +58,11 @@ const char *fwav_last_error(const fwav_ctx *ctx);
 int fwav_ctx_sync(fwav_ctx *ctx);
 /* Select the search kernel for subsequent calls (default FWAV_SEARCH_AUTO). */
 int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl);
+/* Tell subsequent fwav_topk calls that BOTH of their tables were produced by fwav_embed for this range_size (0 =
+ * unknown, the default).  For range_size < 8 at most seven embedding dimensions can be non-zero (fractal.py:154-208)
+ * and the tensor-core search then uses its two-MMA compact split; results are identical either way.  The pipeline
+ * entry points (fwav_compress_*) know their geometry and do not need this. */
+int fwav_ctx_set_search_range_size(fwav_ctx *ctx, int range_size);
 /* Number of kernels this library has launched through `ctx` since creation. */
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx);
 /* Queries the tensor-core search handed from its sampled-threshold fast path to the exact list kernel since

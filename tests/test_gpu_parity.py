@@ -505,46 +505,16 @@ def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_activ
         assert all(sc[j] >= kth - SCORE_TOL for j in out["umma"][0][i])
 
 
-@pytest.mark.parametrize("layout", ["thin3", "thin2", "fat3", "fat2", "sets"])
-@pytest.mark.parametrize("n_q,top_k,mode", [(777, 32, None), (777, 32, "precise"), (5000, 32, None), (1500, 64, None),
-                                            (20000, 32, "hionly")])
-def test_collect_layouts(ctx, monkeypatch, layout, n_q, top_k, mode):
-    """Every layout of the collect pass (FWAV_UMMA_COLLECT) must return what the FFMA kernel returns, candidates and
-    scores (same kind of table as the odd-shapes test; 20 000 queries: full waves plus a split tail wave)."""
-    monkeypatch.setenv("FWAV_UMMA_COLLECT", layout)
-    if mode:
-        monkeypatch.setenv("FWAV_UMMA_MODE", mode)
-    ED = 16
-    n_d = (1 << 17) + 77
-    rng = np.random.default_rng(300 + n_q)
-    e = rng.standard_normal((n_d, ED)).astype(np.float32)
-    for h in (slice(0, 8), slice(8, 16)):
-        e[:, h] /= np.linalg.norm(e[:, h], axis=1, keepdims=True)
-    q = np.ascontiguousarray(e[rng.choice(n_d, n_q, replace=False)] + (rng.standard_normal((n_q, ED)) * 0.05).astype(np.float32))
-    d_e, d_q = ctx.upload(e), ctx.upload(q)
-    out = {}
-    for impl in ("ffma", "umma"):
-        set_impl(ctx, impl)
-        d_cand, d_sc = ctx.alloc(n_q * top_k * 4), ctx.alloc(n_q * top_k * 4)
-        try:
-            ctx.topk(d_q.ptr, n_q, d_e.ptr, n_d, ED, top_k, None, d_cand.ptr, d_sc.ptr)
-        finally:
-            set_impl(ctx, "auto")
-        out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32))
-    assert np.array_equal(out["umma"][0], out["ffma"][0])
-    assert np.array_equal(bits(out["umma"][1]), bits(out["ffma"][1]))
-
-
-@pytest.mark.skipif(os.environ.get("FWAV_TEST_EXPERIMENTAL") != "1",
-                    reason="compact split (FWAV_UMMA_COMPACT=1) was written after round 1's GPU budget was spent: "
-                           "not yet run on a device; set FWAV_TEST_EXPERIMENTAL=1 to try it")
-@pytest.mark.parametrize("n_q,top_k,mode,quad", [(777, 32, "precise", "0"), (777, 32, None, "0"), (3000, 64, None, "0"),
-                                                 (3000, 64, "precise", "1"), (300, 32, "lists", "0")])
-def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
+@pytest.mark.parametrize("n_q,top_k,mode,how", [(777, 32, "precise", "probe"), (777, 32, None, "probe"), (3000, 64, None, "probe"),
+                                                (3000, 64, "precise", "hint"), (300, 32, "lists", "hint")])
+def test_compact_split(ctx, monkeypatch, n_q, top_k, mode, how):
     """Embeddings shaped like range_size 4 (3 live tonal + 4 live transient dimensions, the rest exactly zero):
-    the two-MMA compact split must return what the FFMA kernel returns."""
-    monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
-    monkeypatch.setenv("FWAV_UMMA_COLLECT", "thin3" if quad == "1" else "sets")
+    the two-MMA compact split must return what the FFMA kernel returns -- switched on by the device probe
+    (FWAV_UMMA_COMPACT=1) or by the caller's statement of the geometry (fwav_ctx_set_search_range_size)."""
+    if how == "probe":
+        monkeypatch.setenv("FWAV_UMMA_COMPACT", "1")
+    else:
+        ctx.set_search_range_size(4)
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     ED = 16
@@ -567,6 +537,7 @@ def test_experimental_compact_split(ctx, monkeypatch, n_q, top_k, mode, quad):
         finally:
             set_impl(ctx, "auto")
         out[impl] = (d_cand.to_host((n_q, top_k), np.int32), d_sc.to_host((n_q, top_k), np.float32))
+    ctx.set_search_range_size(0)
     assert np.array_equal(out["umma"][0], out["ffma"][0])
     assert np.array_equal(bits(out["umma"][1]), bits(out["ffma"][1]))
 
@@ -658,9 +629,8 @@ def _music_table(ctx, seconds, seed, tile=4096, N=16, ds=4, ED=16):
     return n_d, d_emb, d_emb.to_host((n_d, ED), np.float32)
 
 
-@pytest.mark.parametrize("top_k,cap,layout", [(32, None, "thin3"), (32, 48, "thin3"), (32, None, "sets"), (32, 48, "fat3"),
-                                              (64, None, "thin3"), (64, 48, "thin3")])
-def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
+@pytest.mark.parametrize("top_k,cap", [(32, None), (32, 48), (64, None), (64, 48)])
+def test_multi_batch_search(ctx, monkeypatch, top_k, cap):
     """The fast path works in batches of 2^20 queries (configs 3 and 4 run 2-21 of them per rank).  FWAV_UMMA_BATCH
     shrinks the batch so that a 5 000-query search crosses batch boundaries seven times: with a pruning mask, a split
     tail wave in every batch and (cap = 48) forced failures whose batch-local indices go through the second chance
@@ -676,7 +646,6 @@ def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
     for impl in ("ffma", "umma"):
         if impl == "umma":
             monkeypatch.setenv("FWAV_UMMA_BATCH", "768")
-            monkeypatch.setenv("FWAV_UMMA_COLLECT", layout)
             if cap:
                 monkeypatch.setenv("FWAV_UMMA_CAP", str(cap))
         set_impl(ctx, impl)
@@ -699,7 +668,7 @@ def test_multi_batch_search(ctx, monkeypatch, top_k, cap, layout):
         kth = np.sort(sc)[-top_k]
         assert set(np.flatnonzero(sc > kth + SCORE_TOL)) <= set(got[0][i].tolist())
         assert all(sc[j] >= kth - SCORE_TOL for j in got[0][i])
-    print(f"multi-batch top_k={top_k} cap={cap} {layout}: 7 batches equal to FFMA; {got[2]} queries took a failure route")
+    print(f"multi-batch top_k={top_k} cap={cap}: 7 batches equal to FFMA; {got[2]} queries took a failure route")
 
 
 def _write_wav_stereo24(path, left, right, rate):
