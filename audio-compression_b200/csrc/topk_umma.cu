@@ -309,6 +309,49 @@ pack_f16_tiles_kernel(const float *__restrict__ src, long long n_rows, long long
     }
 }
 
+// largest squared row norm of a (rows x 16) table, as a float bit pattern (non-negative floats order like their
+// bits); slightly above the exact value whatever the rounding of the sixteen FMAs
+__global__ void __launch_bounds__(256)
+row_norm2_max_kernel(const float *__restrict__ x, long long n_rows, unsigned *__restrict__ out) {
+    float n2 = 0.0f;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        float ss = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ED; k += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ED + k));
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
+        n2 = fmaxf(n2, ss * (1.0f + 2e-6f));
+    }
+    const unsigned u = __reduce_max_sync(kFull, __float_as_uint(n2));
+    if ((threadIdx.x & 31) == 0 && u) atomicMax(out, u);
+}
+
+// ---------------------------------------------------------------------------
+// Error bounds of the two filters ("turn the slacks into bounds").  nq = max |q|, ne = max |e| (row_norm2_max_kernel), B = nq * ne >= sum_k |q_k e_k|.
+//
+// Full split, T = sum_k (hq he + hq le + lq he) on the tensor core, against the canonical float32 score C:
+//   * x = h + l + r with h = fp16(x), l = fp16(x - h): |r| <= 2^-22 |x| in the fp16 normal range, <= 2^-25 below it
+//     (x - h is exact in float32; the fp16 subnormal spacing is 2^-24).  Representation error of the products plus
+//     the dropped lq * le term: <= 3 * 2^-22 * B + 2^-25 * 4 * (nq + ne)          (sum |q_k| <= 4 |q| for 16 components)
+//   * accumulation inside the tensor core is not documented.  Model: the products are exact (22-bit mantissas) and
+//     each of the 3 x 16 = 48 additions behaves no worse than a float32 addition of operands bounded by B:
+//     <= 48 * 2^-23 * B
+//   * C itself is a chain of 16 float32 FMAs: <= 16 * 2^-24 * B
+//   |T - C| <= (3 * 2^-22 + 48 * 2^-23 + 16 * 2^-24) * B + 2^-23 * (nq + ne)  =  7.39e-6 * B + 1.2e-7 * (nq + ne)
+//   (two unit heads, B = 2: 1.5e-5; measured maximum on config 2: 3.9e-7).
+// hi*hi term alone, T1 = sum_k hq he: |hq he - q e| <= (2 * 2^-11 + 2^-22) |q e| per component, plus 16 additions and
+// the chain of C:  |T1 - C| <= (2^-10 + 2^-22 + 16 * 2^-23 + 16 * 2^-24) * B + 2^-23 * (nq + ne)  =  9.796e-4 * B + ...
+//   (B = 2: 1.96e-3; measured 1.1e-3).
+// ---------------------------------------------------------------------------
+constexpr float kFullSlackPerB = 7.39e-6f, kHiSlackPerB = 9.796e-4f, kSlackPerNorm = 1.2e-7f;
+
+// norms: largest squared row norm of the queries [0] and of the domains [1] (row_norm2_max_kernel)
+__device__ __forceinline__ float score_slack(const unsigned *__restrict__ norms, bool hi_only) {
+    const float nq = sqrtf(__uint_as_float(norms[0])) * (1.0f + 1e-6f), ne = sqrtf(__uint_as_float(norms[1])) * (1.0f + 1e-6f);
+    return (hi_only ? kHiSlackPerB : kFullSlackPerB) * nq * ne + kSlackPerNorm * (nq + ne);
+}
+
 // ---------------------------------------------------------------------------
 // Compact split (validated on B200 in round 2: equal to the FFMA kernel on every route, tests/test_gpu_parity.py).
 // With range_size 4 (the reference's default tile_size 1024, BASELINE config 4) only 7 of the 16 embedding
@@ -539,7 +582,7 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
     } while (0)
 
 // HI: only the hi*hi term (one MMA per stage, half the operand bytes).  Its scores are off by up to
-// kHiOnlySlack, which a FILTER can afford when the data leave that much room between the top_k-th score and the
+// score_slack(hi_only), which a FILTER can afford when the data leave that much room between the top_k-th score and the
 // threshold (decided per launch from pass 1, verified per query by finalize_kernel); MODE_LISTS never uses it.
 // CG: CTAs per tensor-core group.  2 = the pair described above (a domain tile is read once per 256 queries).
 // 1 = every CTA on its own (M = 128, the whole 256-domain stage in its shared memory, all barriers local: no relay,
@@ -1002,15 +1045,11 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 // re-scored with the canonical float32 chain, the best top_k are selected
 // best-first (score descending, index ascending) and the result is VERIFIED:
 // a domain outside the collected set has a tensor-core score below theta, hence
-// a canonical score below theta + kScoreSlack; if the top_k-th selected score
-// reaches theta + kScoreSlack nothing outside can belong to the top_k.  Queries
+// a canonical score below theta + slack (score_slack: a bound, not a measurement); if the top_k-th selected score
+// reaches theta + slack nothing outside can belong to the top_k.  Queries
 // that fail (too few candidates, buffer overflow, boundary within the slack) go
 // on the list for the exact MODE_LISTS kernel.
 // ---------------------------------------------------------------------------
-constexpr float kScoreSlack = 4e-6f;    // bound on |split-fp16 tensor-core score - canonical float32 score| (measured max 3.9e-7)
-// hi*hi term alone: inputs rounded to fp16 (relative 2^-11 each), sum |q_k e_k| <= |q||e| <= 2 (two unit heads):
-// 2 * (2^-10 + 2^-22) + subnormal and accumulation terms < 1.96e-3 (measured max 1.1e-3)
-constexpr float kHiOnlySlack = 2e-3f;
 constexpr int kFinWarps = 4;
 constexpr int kFinKeys = 768;          // keys per query the shared-memory path of the first finalize holds (the second chance: all)
 constexpr int kFinRegs = 10;           // candidates per lane the register path of finalize_kernel holds (320 per query)
@@ -1027,7 +1066,8 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x)
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
                 const uint8_t *__restrict__ active, const float *theta, const int32_t *__restrict__ cbuf,
-                const int *__restrict__ ccount, int cap, int parts, int q_index0, float slack, int32_t *__restrict__ cand,
+                const int *__restrict__ ccount, int cap, int parts, int q_index0, const unsigned *__restrict__ norms,
+                int hi_only, int32_t *__restrict__ cand,
                 float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count,
                 float *theta_retry /* may alias theta: a failed query's threshold for the second pass */, int key_cap) {
     extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][key_cap]
@@ -1042,6 +1082,9 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         return;
     }
     unsigned long long *keys = fin_keys + (size_t)warp * key_cap;
+    // how far the filter's score may sit from the canonical one (score_slack): the margin of the proof below
+    const float slack = score_slack(norms, hi_only != 0);
+    const float slack_full = score_slack(norms, false);
     int c = 0;
     bool ok = true, overflow = false;
     for (int p = 0; p < parts; ++p) {                  // parts = 4 column groups x table splits
@@ -1157,16 +1200,17 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         fail_list[atomicAdd(fail_count, 1)] = (int)q + q_index0;
         atomicAdd(fail_count + (overflow ? 1 : n_sel < top_k ? 2 : 3), 1);      // diagnostics: why
         // "boundary": enough candidates, but the last one sits within the slack of theta, so a better one may have
-        // been filtered out.  Every domain that beats `last` scores at least last - kScoreSlack on the tensor
+        // been filtered out.  Every domain that beats `last` scores at least last - slack_full on the tensor
         // cores with the full split: a second collect pass with this threshold finds them all and verifies.
-        if (theta_retry && !overflow && n_sel == want && want > 0) theta_retry[q] = fminf(theta[q], last - 2.0f * kScoreSlack);
+        if (theta_retry && !overflow && n_sel == want && want > 0) theta_retry[q] = fminf(theta[q], last - 2.0f * slack_full);
     }
 }
 
 // After pass 1: how many live queries leave less than `room` between their estimated top_k-th score and theta?
 // Few: the collect pass may filter with the hi*hi term alone.  (A wrong guess costs fallbacks, never correctness.)
 __global__ void count_flat_kernel(const float *__restrict__ theta, const float *__restrict__ theta_hi, long long n_q,
-                                  float room, int *__restrict__ counts) {
+                                  const unsigned *__restrict__ norms, int *__restrict__ counts) {
+    const float room = 2.0f * score_slack(norms, true);
     int flat = 0, live = 0;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n_q; q += (long long)gridDim.x * blockDim.x) {
         const float t = theta[q];
@@ -1450,9 +1494,16 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
     int *d_cnt = nullptr, *d_fail = nullptr;
-    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 4) * sizeof(float), (void **)&d_theta))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 8) * sizeof(float), (void **)&d_theta))) return rc;
     float *d_theta_hi = d_theta + n_q;
     int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
+    // largest row norms of both tables: the error bounds of the filter passes scale with them (score_slack)
+    unsigned *d_norms = reinterpret_cast<unsigned *>(d_theta + 2 * n_q + 4);
+    FWAV_CUDA(ctx, cudaMemsetAsync(d_norms, 0, 2 * sizeof(unsigned), st));
+    row_norm2_max_kernel<<<grid_for(ctx, n_q), 256, 0, st>>>(d_q, n_q, d_norms);
+    FWAV_LAUNCH_CHECK(ctx);
+    row_norm2_max_kernel<<<grid_for(ctx, n_d), 256, 0, st>>>(d_emb, n_d, d_norms + 1);
+    FWAV_LAUNCH_CHECK(ctx);
     int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
     if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
         const int v = atoi(cap_env);
@@ -1497,7 +1548,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         bool hi_only = false;
         if (!(mode_env && !strcmp(mode_env, "precise"))) {
             FWAV_CUDA(ctx, cudaMemsetAsync(d_flat, 0, 2 * sizeof(int), st));
-            count_flat_kernel<<<grid_for(ctx, nq), 256, 0, st>>>(d_theta + q0, d_theta_hi + q0, nq, 2.0f * kHiOnlySlack, d_flat);
+            count_flat_kernel<<<grid_for(ctx, nq), 256, 0, st>>>(d_theta + q0, d_theta_hi + q0, nq, d_norms, d_flat);
             FWAV_LAUNCH_CHECK(ctx);
             int h_flat[2] = {0, 0};
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_flat, d_flat, sizeof h_flat, cudaMemcpyDeviceToHost, st));
@@ -1507,8 +1558,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.02 * h_flat[1];
             if (mode_env && !strcmp(mode_env, "hionly")) hi_only = true;
             if (getenv("FWAV_UMMA_VERBOSE"))
-                fprintf(stderr, "[fwav] search batch at %lld: %d of %d live queries leave < %.1e between their top_k-th score and theta: %s collect pass\n",
-                        q0, h_flat[0], h_flat[1], 2.0 * kHiOnlySlack, hi_only ? "hi*hi-only" : "full-split");
+                fprintf(stderr, "[fwav] search batch at %lld: %d of %d live queries leave less than twice the hi*hi error bound between their top_k-th score and theta: %s collect pass\n",
+                        q0, h_flat[0], h_flat[1], hi_only ? "hi*hi-only" : "full-split");
         }
         ctx->search_hi_only = hi_only;
         if ((rc = mark(ctx, slot, 2, st))) return rc;
@@ -1584,7 +1635,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             finalize_kernel<<<(unsigned)((ax.n_q + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
                               fin_smem, st>>>(
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
-                hi_only ? kHiOnlySlack : kScoreSlack, d_cand + (q0 + qoff) * top_k,
+                d_norms, hi_only ? 1 : 0, d_cand + (q0 + qoff) * top_k,
                 d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
                 d_theta + q0 + qoff, key_cap);
             FWAV_LAUNCH_CHECK(ctx);
@@ -1655,7 +1706,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     if (fin_smem > 48 * 1024)
                         FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
                     finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
-                        d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, kScoreSlack,
+                        d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, d_norms, 0,
                         d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, parts * rcap);
                     FWAV_LAUNCH_CHECK(ctx);
                     int h_fail2[4] = {0, 0, 0, 0};

@@ -614,7 +614,8 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
         return {"sampled": int(t.sum()), "winner_in_brute_force_top_k": int(t[0]), "not": int(t[1]), "pruned": int(t[2])}
 
     # ---- c3 + c5 ----
-    info, res, (t_sig, t_rng, tile, k, N) = timed_compress("c3", 1.0, 1)
+    xs = float(os.environ.get("FWAV_BENCH_EXTRAS_SCALE", "1.0"))     # debug: shorten the extra workloads
+    info, res, (t_sig, t_rng, tile, k, N) = timed_compress("c3", 1.0 * xs, 1)
     info["verified"] = verify_sample(res, t_rng, tile, k, N)
     out["c3"] = info
     idx, s, o, sym, err, dom = res
@@ -643,7 +644,7 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
     torch.cuda.empty_cache()
     # ---- c4 at 1/4 length, if the run is still young ----
     if time.time() - t_start < 420:
-        info, res, (t_sig, t_rng, tile, k, N) = timed_compress("c4", 0.25, 1)
+        info, res, (t_sig, t_rng, tile, k, N) = timed_compress("c4", 0.25 * xs, 1)
         info["verified"] = verify_sample(res, t_rng, tile, k, N)
         out["c4_quarter"] = info
     ctx.set_search_range_size(0)
