@@ -223,6 +223,13 @@ int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl) {
     return FWAV_OK;
 }
 
+int fwav_ctx_set_embedding(fwav_ctx *ctx, int kind) {
+    if (!ctx) return FWAV_ERR_INVALID;
+    FWAV_REQUIRE(ctx, kind == FWAV_EMBED_TWO_HEAD || kind == FWAV_EMBED_TONAL, "unknown embedding kind %d", kind);
+    ctx->embed_kind = kind;
+    return FWAV_OK;
+}
+
 int fwav_ctx_set_search_range_size(fwav_ctx *ctx, int range_size) {
     if (!ctx) return FWAV_ERR_INVALID;
     FWAV_REQUIRE(ctx, range_size >= 0 && range_size <= fwm::kMaxRangeSize, "range_size %d out of range", range_size);

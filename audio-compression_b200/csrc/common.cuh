@@ -34,6 +34,7 @@ struct fwav_ctx {
     // entry points around their own search, or by fwav_ctx_set_search_range_size; tells the tensor-core search
     // which embedding dimensions can be non-zero at all (fractal.py:154-208) without a device round trip.
     int search_range_size = 0;
+    int embed_kind = FWAV_EMBED_TWO_HEAD;     // what fwav_embed / the pipeline compute (fwav_ctx_set_embedding)
 
     // embedding matrices cached per (N, half)
     int emb_N = 0, emb_half = 0;

@@ -104,6 +104,18 @@ embed_generic_kernel(const float *__restrict__ rows, long long n_rows, int N, in
     }
 }
 
+// tonal-only form (fwav_ctx_set_embedding(ctx, FWAV_EMBED_TONAL)): tile_embedding(row, k = emb_dim)
+__global__ void __launch_bounds__(128)
+embed_tonal_kernel(const float *__restrict__ rows, long long n_rows, int N, int emb_dim,
+                   const double *__restrict__ tonal, float *__restrict__ emb) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        const float *x = rows + r * N;
+        auto row = [&](int i) { return __ldg(x + i); };
+        fwm::embed_tonal_row(row, N, emb_dim, tonal, emb + r * emb_dim);
+    }
+}
+
 template <int N, int HALF>
 int launch_static(fwav_ctx *ctx, const float *d_rows, int64_t rows, float *d_emb, cudaStream_t st) {
     const FwavEmbedTables t = fwav_make_embed_tables(N, HALF);
@@ -142,10 +154,20 @@ int fwav_embed_tables_device(fwav_ctx *ctx, int N, int half) {
 int fwav_launch_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int N, int emb_dim,
                       float *d_emb, cudaStream_t st) {
     FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
-    FWAV_REQUIRE(ctx, emb_dim >= 2 && emb_dim <= 256 && emb_dim % 2 == 0,
+    FWAV_REQUIRE(ctx, emb_dim >= 2 && emb_dim <= 256 && (emb_dim % 2 == 0 || ctx->embed_kind == FWAV_EMBED_TONAL),
                  "emb_dim %d must be even and in [2, 256] (the reference breaks on odd values, "
                  "fractal.py:275)", emb_dim);
     if (rows == 0) return FWAV_OK;
+    if (ctx->embed_kind == FWAV_EMBED_TONAL) {
+        int rc = fwav_embed_tables_device(ctx, N, emb_dim);     // "half" = all of the emb_dim tonal rows
+        if (rc) return rc;
+        long long need = (rows + 127) / 128;
+        long long cap = (long long)ctx->num_sms * 8;
+        const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+        embed_tonal_kernel<<<grid, 128, 0, st>>>(d_rows, rows, N, emb_dim, ctx->d_tonal, d_emb);
+        FWAV_LAUNCH_CHECK(ctx);
+        return FWAV_OK;
+    }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_rows) | reinterpret_cast<uintptr_t>(d_emb)) & 15) == 0;
     if (emb_dim == 16 && aligned) {
         if (N == 4) return launch_static<4, 8>(ctx, d_rows, rows, d_emb, st);

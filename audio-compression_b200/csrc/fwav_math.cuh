@@ -131,6 +131,24 @@ FWAV_HD void embed_row(Row x, int N, int half, const double *tonal_m, const doub
     }
 }
 
+// tile_embedding(x, k) on its own (fractal.py:178-208, the EMBED_K = 32 form the README describes): the tonal head
+// with k coefficients.  tonal_m: k x N doubles as above.
+template <class Row>
+FWAV_HD void embed_tonal_row(Row x, int N, int k_dim, const double *tonal_m, float *out) {
+    double ssq = 0.0;
+    for (int k = 0; k < k_dim; ++k) {
+        double acc = 0.0;
+        const double *m = tonal_m + (long long)k * N;
+        for (int n = 0; n < N; ++n) acc = fma((double)x(n), m[n], acc);
+        float v = (float)acc;
+        out[k] = v;
+        ssq += (double)v * (double)v;
+    }
+    float nrm = npm::sqrt((float)ssq);
+    if (nrm > 1e-8f)
+        for (int k = 0; k < k_dim; ++k) out[k] = npm::div(out[k], nrm);
+}
+
 // ---------------------------------------------------------------------------
 // A4  canonical float32 score: one FMA chain in ascending k.
 // ---------------------------------------------------------------------------

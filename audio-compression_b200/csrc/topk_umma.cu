@@ -1421,7 +1421,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
             live = h_mask[0] & h_mask[1];    // a dimension dead on either side adds exactly 0 to every score
             known = true;
-        } else if (allowed && ctx->search_range_size > 0) {
+        } else if (allowed && ctx->search_range_size > 0 && ctx->embed_kind == FWAV_EMBED_TWO_HEAD) {
             // tables built by fwav_embed for this range_size: min(8, N - 1) tonal and min(8, N) transient dimensions
             const int N = ctx->search_range_size;
             live = 0;

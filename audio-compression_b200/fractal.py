@@ -58,8 +58,11 @@ def _empty_result(range_size, tile_size, domain_step, energy_thresh, original_le
             domain_step, energy_thresh, original_len)
 
 
+_in_tonal = [False]     # compress_audio_arrays re-enters itself once with the context switched to the tonal embedding
+
+
 def compress_audio_arrays(signal, tile_size=1024, emb_dim=16, energy_thresh=1e-4, fast_mode=True,
-                          k=None, query_mode=None, ctx=None):
+                          k=None, query_mode=None, ctx=None, embedding=None):
     """compress_audio without the Python tuple list: returns
     (MatchArrays, domains, n_ranges, range_size, tile_size, domain_step,
     energy_thresh, original_len)."""
@@ -71,6 +74,20 @@ def compress_audio_arrays(signal, tile_size=1024, emb_dim=16, energy_thresh=1e-4
     if query_mode is None:
         query_mode = 1 if os.environ.get("FWAV_QUERY_MODE", "reference") == "range" else 0
     kk = top_k if k is None else k
+    if embedding is None:
+        embedding = os.environ.get("FWAV_EMBEDDING", "two_head")
+    if embedding not in ("two_head", "tonal"):
+        raise ValueError(f"embedding must be 'two_head' (the reference's live path) or 'tonal' (tile_embedding), got {embedding!r}")
+    if embedding == "tonal" and not _in_tonal[0]:
+        # the "fixed" mode of the docs: tile_embedding(k = emb_dim) (fractal.py:178-208; EMBED_K = 32 there)
+        ctx = ctx or _lib.default_context(_device())
+        ctx.set_embedding(_lib.EMBED_TONAL)
+        _in_tonal[0] = True
+        try:
+            return compress_audio_arrays(signal, tile_size, emb_dim, energy_thresh, fast_mode, k, query_mode, ctx, "tonal")
+        finally:
+            _in_tonal[0] = False
+            ctx.set_embedding(_lib.EMBED_TWO_HEAD)
     if not (signal[:4096].any() or signal.any()):
         return empty       # digital silence: every frame energy is 0, the gate never opens (fractal.py:1083-1093)
     if n_domains > 0 and original_len >= 10 * range_size:

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FWAV_LIB") or os.path.join(_HERE, "libfwav_b200.so")    # FWAV_LIB: experiment builds
 
 SEARCH_AUTO, SEARCH_FFMA, SEARCH_UMMA = 0, 1, 2
+EMBED_TWO_HEAD, EMBED_TONAL = 0, 1
 
 c_ctx = C.c_void_p
 c_ptr = C.c_void_p
@@ -38,6 +39,7 @@ SIGNATURES = [
     ("fwav_last_error", C.c_char_p, [c_ctx]),
     ("fwav_ctx_sync", C.c_int, [c_ctx]),
     ("fwav_ctx_set_search_impl", C.c_int, [c_ctx, C.c_int]),
+    ("fwav_ctx_set_embedding", C.c_int, [c_ctx, C.c_int]),
     ("fwav_ctx_set_search_range_size", C.c_int, [c_ctx, C.c_int]),
     ("fwav_ctx_launch_count", i64, [c_ctx]),
     ("fwav_ctx_search_fallbacks", i64, [c_ctx]),
@@ -223,6 +225,10 @@ class Context:
 
     def set_search_impl(self, impl):
         self._check(self.lib.fwav_ctx_set_search_impl(self.h, int(impl)))
+
+    def set_embedding(self, kind):
+        """EMBED_TWO_HEAD (the reference's live path) or EMBED_TONAL (tile_embedding with k = emb_dim)."""
+        self._check(self.lib.fwav_ctx_set_embedding(self.h, int(kind)))
 
     def set_search_range_size(self, range_size):
         self._check(self.lib.fwav_ctx_set_search_range_size(self.h, int(range_size)))

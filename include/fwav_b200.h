@@ -48,6 +48,13 @@ typedef enum fwav_search_impl {
     FWAV_SEARCH_UMMA = 2   /* tcgen05 split-fp16 kernels (sampled threshold, collect, exact FP32 finalize; list kernel) */
 } fwav_search_impl;
 
+/* Which embedding fwav_embed and the pipeline entry points compute. */
+typedef enum fwav_embedding {
+    FWAV_EMBED_TWO_HEAD = 0, /* multi_head_embedding(tile, emb_dim/2, emb_dim/2) (fractal.py:166-175): the reference's LIVE path */
+    FWAV_EMBED_TONAL = 1     /* tile_embedding(tile, k = emb_dim) (fractal.py:178-208): the DCT-II / DC-removed / high-frequency-
+                                weighted / L2-normalised embedding the README and the north star describe (EMBED_K = 32) */
+} fwav_embedding;
+
 const char *fwav_version(void);
 int fwav_device_count(void);
 
@@ -58,6 +65,9 @@ const char *fwav_last_error(const fwav_ctx *ctx);
 int fwav_ctx_sync(fwav_ctx *ctx);
 /* Select the search kernel for subsequent calls (default FWAV_SEARCH_AUTO). */
 int fwav_ctx_set_search_impl(fwav_ctx *ctx, int impl);
+/* Select the embedding for subsequent calls (default FWAV_EMBED_TWO_HEAD).  Together with query_mode = 1 of the
+ * pipeline entry points this is the north star's "fixed" mode: true range embeddings, tile_embedding with EMBED_K. */
+int fwav_ctx_set_embedding(fwav_ctx *ctx, int kind);
 /* Tell subsequent fwav_topk calls that BOTH of their tables were produced by fwav_embed for this range_size (0 =
  * unknown, the default).  For range_size < 8 at most seven embedding dimensions can be non-zero (fractal.py:154-208)
  * and the tensor-core search then uses its two-MMA compact split; results are identical either way.  The pipeline

@@ -182,9 +182,13 @@ def transient_head(rows, k, fast_norm=False):
     return out
 
 
-def embed_rows(rows, emb_dim=16, fast_norm=False):
+def embed_rows(rows, emb_dim=16, fast_norm=False, head="two_head"):
     """`multi_head_embedding(tile, emb_dim//2, emb_dim//2)` for every row
-    (fractal.py:166-175 called from :271-277): [tonal | transient | zero pad]."""
+    (fractal.py:166-175 called from :271-277): [tonal | transient | zero pad].
+    head="tonal": `tile_embedding(tile, k=emb_dim)` (fractal.py:178-208), the form the README describes
+    (EMBED_K = 32); not on the reference's live path."""
+    if head == "tonal":
+        return tonal_head(rows, emb_dim, fast_norm)
     half = emb_dim // 2
     rows = np.asarray(rows, dtype=np.float32)
     ton = tonal_head(rows, half, fast_norm)
@@ -289,7 +293,7 @@ def affine_match(ranges, cand, domains, s_clip=16.0, want_all=False):
 # A8  compress: single-process replay of the live path      fractal.py:1045-1256
 # ----------------------------------------------------------------------------
 def compress(signal, tile_size=1024, emb_dim=16, top_k=DEFAULT_TOP_K, energy_thresh=1e-4,
-             fast_mode=True, batch=512, query_mode="reference", want_intermediates=False):
+             fast_mode=True, batch=512, query_mode="reference", want_intermediates=False, head="two_head"):
     """Replay of compress_audio without processes or queues.
 
     query_mode="reference": q_i = E[i] (the live aliasing, fractal.py:1190-1195;
@@ -310,13 +314,13 @@ def compress(signal, tile_size=1024, emb_dim=16, top_k=DEFAULT_TOP_K, energy_thr
     domains = build_domains(signal, tile_size, rsz, step)
     if len(domains) == 0:                                           # :1130
         return empty
-    embs = embed_rows(domains, emb_dim)
+    embs = embed_rows(domains, emb_dim, head=head)
     if query_mode == "reference":
         if n_rng > len(domains):
             raise ValueError("mmap length is greater than file size")   # what :1190 raises
         queries = embs[:n_rng]
     elif query_mode == "range":
-        queries = embed_rows(prep["ranges"], emb_dim)
+        queries = embed_rows(prep["ranges"], emb_dim, head=head)
     else:
         raise ValueError(query_mode)
     cand = candidates_for_ranges(prep["ranges"], queries, embs, top_k, energy_thresh, fast_mode)

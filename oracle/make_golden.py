@@ -246,8 +246,26 @@ def main_t2048():
     print("music_t2048: ranges", len(g["idx"]), "domains", len(g["domains"]))
 
 
+def main_tile_embedding():
+    """Round 2: the reference's tile_embedding(x, k=EMBED_K=32) (fractal.py:178-208) on its own -- the embedding the
+    README / north star describe, not on the live path -- for rows of 4, 8, 16 and 40 samples."""
+    ref = load_reference()
+    rng = np.random.default_rng(32)
+    out = {}
+    for n in (4, 8, 16, 40):
+        rows = (rng.standard_normal((64, n)) * 10.0 ** rng.uniform(-2, 4, (64, 1))).astype(np.float32)
+        rows[0] = 0.0                      # norm below 1e-8: left unnormalised
+        rows[1] = 123.0                    # constant tile: DC only, every kept coefficient ~0
+        out[f"rows_{n}"] = rows
+        out[f"emb_{n}"] = np.stack([ref.tile_embedding(r, k=ref.EMBED_K) for r in rows]).astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "tile_embedding_k32.npz"), **out)
+    print("tile_embedding_k32:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "t2048":
         main_t2048()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tile_embedding":
+        main_tile_embedding()
     else:
         main()

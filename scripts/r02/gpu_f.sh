@@ -3,9 +3,9 @@
 # shortened extras, sharded decode timings
 set +e
 O=gpurun_out; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "adversarial or query_mode or search or multi_batch or compact or config" > $O/r02f_tests.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "adversarial or query_mode or fixed_mode or search or multi_batch or compact or config" > $O/r02f_tests.txt 2>&1
 echo "tests: rc=$? $(tail -1 $O/r02f_tests.txt)"; grep -E "^(FAILED|ERROR)|Error" $O/r02f_tests.txt | head
-python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "adversarial or query_mode" 2>&1 | grep -E "adversarial|query_mode=range" | head
+python -m pytest tests/test_gpu_parity.py -m gpu -q -s -k "adversarial or query_mode or fixed_mode" 2>&1 | grep -E "adversarial|query_mode=range|fixed mode" | head
 timeout 200 python scripts/time_topk.py 1.0 umma 3 2>/dev/null | cut -c1-330
 FWAV_BENCH_EXTRAS=1 FWAV_BENCH_EXTRAS_SCALE=0.1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > $O/r02f_bench_n2.json 2> $O/r02f_bench_n2.err
 echo "bench n2 rc=$?"; tail -3 $O/r02f_bench_n2.err | cut -c1-300

@@ -53,6 +53,15 @@ void hh_embed(const float *rows, long long n_rows, int N, int emb_dim, float *ou
     }
 }
 
+void hh_embed_tonal(const float *rows, long long n_rows, int N, int k, float *out) {
+    FwavEmbedTables t = fwav_make_embed_tables(N, k);
+    for (long long r = 0; r < n_rows; ++r) {
+        const float *x = rows + r * N;
+        auto row = [&](int i) { return x[i]; };
+        fwm::embed_tonal_row(row, N, k, t.tonal.data(), out + r * k);
+    }
+}
+
 void hh_activity(const float *ranges, long long n_r, int N, double thr, int fast, uint8_t *act) {
     for (long long i = 0; i < n_r; ++i) {
         const float *r = ranges + i * N;

@@ -45,6 +45,12 @@ class Harness:
     def __init__(self):
         self.lib = load()
 
+    def embed_tonal(self, rows, k=32):
+        rows = f32(rows)
+        out = np.empty((rows.shape[0], k), np.float32)
+        self.lib.hh_embed_tonal(_p(rows), C.c_longlong(rows.shape[0]), C.c_int(rows.shape[1]), C.c_int(k), _p(out))
+        return out
+
     def prestep(self, sig, N, thr=1e-4):
         sig = f32(sig)
         n = len(sig)

@@ -90,3 +90,11 @@ def test_reference_quirks():
     res = O.compress(np.ones(500, np.float32) * 1000, tile_size=1024)
     assert res["n_ranges"] == 0 and res["original_len"] == 500
     assert O.derive_geometry(4096) == (16, 4) and O.derive_geometry(128) == (4, 1)
+
+
+def test_tile_embedding_k32_pinned():
+    """The tonal-only embedding (the README's EMBED_K = 32 form) against the reference's own tile_embedding."""
+    g = golden("tile_embedding_k32")
+    for n in (4, 8, 16, 40):
+        got = O.embed_rows(g[f"rows_{n}"], 32, head="tonal")
+        assert np.array_equal(bits(got), bits(g[f"emb_{n}"])), n
