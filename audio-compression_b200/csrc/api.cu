@@ -366,6 +366,22 @@ int fwav_decode_iter_gated(fwav_ctx *ctx, const float *d_domains, int64_t n_doma
                                    s_clip, s_damping, first, d_cur, d_next, d_sums, d_state, fwav_stream(ctx, stream));
 }
 
+int fwav_decode_iter_bcast(fwav_ctx *ctx, const float *d_domains, int64_t n_domains, const int32_t *d_idx,
+                           const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_ranges, int range_size,
+                           double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
+                           double *d_sums, fwav_decode_state *d_state, void *const *targets, int n_targets,
+                           int multimem, int64_t target_offset, void *stream) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, d_sums && d_state && (n_ranges == 0 || (d_domains && d_idx && d_s && d_o && d_sym && d_next)),
+                 "null buffer");
+    FWAV_REQUIRE(ctx, first || n_ranges == 0 || d_cur, "d_cur is required after the first iteration");
+    FWAV_REQUIRE(ctx, n_targets >= 1 && n_targets <= 8 && targets && (!multimem || n_targets == 1),
+                 "1..8 broadcast targets (exactly one multicast address)");
+    return fwav_launch_decode_iter(ctx, d_domains, n_domains, d_idx, d_s, d_o, d_sym, n_ranges, range_size,
+                                   s_clip, s_damping, first, d_cur, d_next, d_sums, d_state, fwav_stream(ctx, stream),
+                                   targets, n_targets, multimem, target_offset);
+}
+
 int fwav_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double convergence_eps,
                          fwav_decode_state *d_state, void *stream) {
     FWAV_ENTER(ctx);

@@ -54,7 +54,7 @@ enum {
     WS_UMMA_THETA, WS_UMMA_CBUF, WS_UMMA_CNT, WS_UMMA_FAIL, WS_UMMA_FB, WS_UMMA_PARTS, WS_FFMA_PARTS, WS_UMMA_TAIL,
     // device mirrors of the host-buffer entry points
     WS_H_SIGNAL, WS_H_RANGES, WS_H_DOMAINS, WS_H_EMB, WS_H_MATCH, WS_H_OUT,
-    WS_PRESTEP, WS_DECODE_TILES,
+    WS_PRESTEP, WS_DECODE_TILES, WS_UMMA_NORMS, WS_UMMA_LFAIL,
     WS_COUNT
 };
 static_assert(WS_COUNT <= 32, "grow fwav_ctx::ws");
@@ -114,7 +114,8 @@ int fwav_launch_decode(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const
 int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
                             const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
                             double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
-                            double *d_sums, void *d_user_state, cudaStream_t st);
+                            double *d_sums, void *d_user_state, cudaStream_t st, void *const *targets = nullptr,
+                            int n_targets = 0, int multimem = 0, int64_t target_offset = 0);
 int fwav_launch_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double eps, void *d_state,
                                 cudaStream_t st);
 

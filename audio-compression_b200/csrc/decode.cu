@@ -160,12 +160,35 @@ decode_prepare_kernel(const float *__restrict__ domains, long long n_d, const in
 // reconstruction of those ranges are 32 * NT contiguous floats each, moved as float4 with consecutive lanes on
 // consecutive addresses, and transposed through shared memory (rows padded to NT + 4 floats: a lane's row reads
 // hit distinct banks) so that lane r holds range r for fwm::decode_range.
-template <int NT>
+// BC: the fused compute + collective form (north star: "the reconstruction buffer is all-gathered over NVLink each
+// iteration").  Every output float4 is ALSO stored into the full reconstruction buffer of every GPU, at this rank's
+// offset: either one multimem.st to the NVSwitch multicast address of the symmetric buffer (the switch replicates
+// it to all GPUs: the SM issues one store, NVLink carries the slice once) or one plain store per peer pointer.
+// The exchange so overlaps the compute tile by tile and no all-gather follows the kernel.
+struct BcastTargets {
+    float *p[8];
+    int n;
+    int multimem;
+    long long off4;        // this rank's slice, in float4, inside the full buffer
+};
+__device__ __forceinline__ void bcast_store(const BcastTargets &tg, long long j, float4 v) {
+    if (tg.multimem) {
+        asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float4 *>(tg.p[0]) + tg.off4 + j),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (t < tg.n) st_stream_f4(reinterpret_cast<float4 *>(tg.p[t]) + tg.off4 + j, v);
+    }
+}
+
+template <int NT, bool BC>
 __global__ void __launch_bounds__(kThreads)
 decode_stream_kernel(const float *__restrict__ tiles, const float *__restrict__ s_use, const float *__restrict__ o_use,
                      long long n_r, float clipf, int damped, float one_minus_damp, float damp, int first,
                      const float *__restrict__ cur, float *__restrict__ nxt, const DecodeState *__restrict__ state,
-                     double *__restrict__ partials) {
+                     double *__restrict__ partials, const BcastTargets tg) {
     if (state->done) return;
     constexpr int V = NT / 4;                   // float4 per range
     constexpr int kRow = NT + 4;                // padded row, in floats
@@ -232,7 +255,11 @@ decode_stream_kernel(const float *__restrict__ tiles, const float *__restrict__ 
             for (int k = 0; k < NT; ++k) w[k] = 0.0f;
         }
         if (V == 1) {
-            if (i < n_r) st_stream_f4(reinterpret_cast<float4 *>(nxt) + base4 + lane, make_float4(w[0], w[1], w[2], w[3]));
+            if (i < n_r) {
+                const float4 v = make_float4(w[0], w[1], w[2], w[3]);
+                st_stream_f4(reinterpret_cast<float4 *>(nxt) + base4 + lane, v);
+                if (BC) bcast_store(tg, base4 + lane, v);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < V; ++k)
@@ -242,7 +269,11 @@ decode_stream_kernel(const float *__restrict__ tiles, const float *__restrict__ 
             for (int k = 0; k < V; ++k) {
                 const int f = k * 32 + lane;
                 const long long j = base4 + f;
-                if (j < total4) st_stream_f4(reinterpret_cast<float4 *>(nxt) + j, *reinterpret_cast<const float4 *>(my + (f / V) * kRow + (f % V) * 4));
+                if (j < total4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(my + (f / V) * kRow + (f % V) * 4);
+                    st_stream_f4(reinterpret_cast<float4 *>(nxt) + j, v);
+                    if (BC) bcast_store(tg, j, v);
+                }
             }
             __syncwarp();
         }
@@ -361,8 +392,15 @@ int launch_prepare(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int
 
 int launch_stream(fwav_ctx *ctx, const Prepared &p, int64_t n_r, int N, float clipf, int damped, float omd, float dmp,
                   int first, const float *cur, float *nxt, const DecodeState *d_state, double *d_part, int grid,
-                  cudaStream_t st) {
-#define FWAV_STRM(NT) decode_stream_kernel<NT><<<grid, kThreads, 0, st>>>(p.tiles, p.s_use, p.o_use, n_r, clipf, damped, omd, dmp, first, cur, nxt, d_state, d_part)
+                  cudaStream_t st, const BcastTargets *tg = nullptr) {
+    const BcastTargets none = {};
+#define FWAV_STRM(NT)                                                                                                         \
+    do {                                                                                                                      \
+        if (tg) decode_stream_kernel<NT, true><<<grid, kThreads, 0, st>>>(p.tiles, p.s_use, p.o_use, n_r, clipf, damped, omd, \
+                                                                          dmp, first, cur, nxt, d_state, d_part, *tg);        \
+        else decode_stream_kernel<NT, false><<<grid, kThreads, 0, st>>>(p.tiles, p.s_use, p.o_use, n_r, clipf, damped, omd,   \
+                                                                        dmp, first, cur, nxt, d_state, d_part, none);        \
+    } while (0)
     if (N == 4) FWAV_STRM(4);
     else if (N == 8) FWAV_STRM(8);
     else if (N == 16) FWAV_STRM(16);
@@ -379,8 +417,10 @@ int launch_stream(fwav_ctx *ctx, const Prepared &p, int64_t n_r, int N, float cl
 int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, const int32_t *d_idx,
                             const float *d_s, const float *d_o, const uint8_t *d_sym, int64_t n_r, int N,
                             double s_clip, double s_damping, int first, const float *d_cur, float *d_next,
-                            double *d_sums, void *d_user_state, cudaStream_t st) {
+                            double *d_sums, void *d_user_state, cudaStream_t st, void *const *targets, int n_targets,
+                            int multimem, int64_t target_offset) {
     FWAV_REQUIRE(ctx, N >= 1 && N <= fwm::kMaxRangeSize, "range_size %d out of range", N);
+    FWAV_REQUIRE(ctx, n_targets >= 0 && n_targets <= 8 && (n_targets == 0 || targets), "0..8 broadcast targets");
     if (n_r == 0) {
         FWAV_CUDA(ctx, cudaMemsetAsync(d_sums, 0, 2 * sizeof(double), st));
         return FWAV_OK;
@@ -409,11 +449,22 @@ int fwav_launch_decode_iter(fwav_ctx *ctx, const float *d_domains, int64_t n_d, 
         if ((rc = prepared_buffers(ctx, n_r, N, &p))) return rc;
         if (first && (rc = launch_prepare(ctx, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, N, p, d_state, grid, st))) return rc;
         const int sgrid = (int)(((n_r + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32) < cap ? ((n_r + 31) / 32 + kThreads / 32 - 1) / (kThreads / 32) : cap);
-        if ((rc = launch_stream(ctx, p, n_r, N, clipf, damped, omd, dmp, first, d_cur, d_next, d_state, d_part, sgrid, st))) return rc;
+        BcastTargets tg = {};
+        if (n_targets > 0) {
+            FWAV_REQUIRE(ctx, (target_offset * 4) % 16 == 0, "broadcast offset must be a multiple of four samples");
+            for (int t = 0; t < n_targets; ++t) tg.p[t] = static_cast<float *>(targets[t]);
+            tg.n = n_targets;
+            tg.multimem = multimem;
+            tg.off4 = target_offset / 4;
+        }
+        if ((rc = launch_stream(ctx, p, n_r, N, clipf, damped, omd, dmp, first, d_cur, d_next, d_state, d_part, sgrid, st,
+                                n_targets > 0 ? &tg : nullptr)))
+            return rc;
         decode_sum_partials_kernel<<<1, 32, 0, st>>>(d_part, sgrid, d_sums);
         FWAV_LAUNCH_CHECK(ctx);
         return FWAV_OK;
     }
+    FWAV_REQUIRE(ctx, n_targets == 0, "the fused broadcast needs range_size 4, 8, 16 or 32 and 16-byte aligned buffers");
 #define FWAV_DEC(NT)                                                                                   \
     decode_iter_kernel<NT><<<grid, kThreads, 0, st>>>(d_domains, d_idx, d_s, d_o, d_sym, n_r, N, clipf, \
                                                       damped, omd, dmp, first, d_cur, d_next, d_state, d_part, (long long)n_d)

@@ -29,7 +29,8 @@
 //     reduce each 32-column chunk to its maximum with 3-input max instructions and
 //     compare it with the row's threshold; only chunks that reach it do more.
 //
-// MODE_LISTS keeps an exact running top-K in shared memory (small tables, fallback);
+// MODE_LISTS keeps a running top-48 by tensor-core score in shared memory and PROVES per row that the exact top-K is
+// among them (rows that cannot -- a boundary crowded within the filter's error -- go to the FFMA kernel); small tables, fallback;
 // MODE_THETA + MODE_COLLECT + finalize_kernel are the fast path: a per-query
 // threshold from a strided sample of the table, one scan that only appends the
 // indices of the domains that reach it, then an exact re-score with a proof that
@@ -119,6 +120,9 @@ struct ScanArgs {
     int cap;
     int dbg;
     long long *trace;          // profiling: clock64 stamps of pair 0's leader CTA, [stage][8] (dbg bit 64)
+    // MODE_LISTS: rows whose kept lists cannot PROVE the top_k (see lists_unsafe) are appended here for the FFMA kernel
+    int *lfail_list, *lfail_count;
+    const unsigned *norms;     // largest squared row norms (row_norm2_max_kernel): the error bound of the filter scores
 };
 
 
@@ -991,6 +995,11 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 if (qq >= n_q) break;
                 unsigned long long *keys = rows + (size_t)(row0 + r) * 2 * kCap;      // both column halves, contiguous
                 const float *qv = a.Q + qq * ED;
+                // what an EVICTED candidate of either half can have scored at most on the tensor cores: the half's
+                // 48th kept key (-inf while that list is not full: nothing was evicted from it)
+                const float evict_max = fmaxf(unorder_bits((uint32_t)(keys[kKeep - 1] >> 32)),
+                                              unorder_bits((uint32_t)(keys[kCap + kKeep - 1] >> 32)));
+                __syncwarp();
                 // canonical score (ascending-k float32 FMA chain) of every kept candidate
                 unsigned long long k[kPerLane];
 #pragma unroll
@@ -1015,14 +1024,27 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 #pragma unroll
                     for (int i = 0; i < kPerLane; ++i) rk[i] += ko > k[i] ? 1 : 0;
                 }
+                float kth = INFINITY;        // canonical score of the last returned candidate (-inf: fewer than top_k exist)
 #pragma unroll
                 for (int i = 0; i < kPerLane; ++i) {
                     if (rk[i] < top_k) {
                         const bool has = (uint32_t)(k[i] >> 32) != kNegInfBits;
                         a.cand[qq * top_k + rk[i]] = has ? (int)(0xFFFFFFFFu - (uint32_t)k[i]) : -1;
                         if (a.scores) a.scores[qq * top_k + rk[i]] = has ? unorder_bits((uint32_t)(k[i] >> 32)) : -INFINITY;
+                        if (rk[i] == top_k - 1) kth = has ? unorder_bits((uint32_t)(k[i] >> 32)) : -INFINITY;
                     }
                 }
+                kth = fminf(kth, __shfl_xor_sync(kFull, kth, 16));
+                kth = fminf(kth, __shfl_xor_sync(kFull, kth, 8));
+                kth = fminf(kth, __shfl_xor_sync(kFull, kth, 4));
+                kth = fminf(kth, __shfl_xor_sync(kFull, kth, 2));
+                kth = fminf(kth, __shfl_xor_sync(kFull, kth, 1));
+                // The lists are kept by TENSOR-CORE score.  An evicted candidate scored at most evict_max there, hence
+                // at most evict_max + slack canonically: unless the top_k-th canonical score beats that, a true member
+                // of the top_k may have been evicted (more than 16 candidates crowding the boundary within the filter's
+                // error) and the row goes to the FFMA kernel.
+                if (lane == 0 && a.lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(a.norms, false)))
+                    a.lfail_list[atomicAdd(a.lfail_count, 1)] = (int)qq;
                 __syncwarp();
             }
             }
@@ -1249,7 +1271,8 @@ __global__ void scatter_cand_kernel(const int32_t *__restrict__ src, const float
 __global__ void __launch_bounds__(128)
 merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, int n_split, int top_k,
                    const uint8_t *__restrict__ active, unsigned long long *__restrict__ parts, int32_t *__restrict__ cand,
-                   float *__restrict__ scores) {
+                   float *__restrict__ scores, const unsigned *__restrict__ norms, int *__restrict__ lfail_list,
+                   int *__restrict__ lfail_count) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * 4 + warp;
     if (q >= n_q) return;
@@ -1263,6 +1286,13 @@ merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, lon
     unsigned long long *keys = parts + q * n_split * (2 * kCap);
     const int c = n_split * 2 * kCap;
     const float *qv = Q + q * ED;
+    // the most an evicted candidate of any (split, column half) list can have scored on the tensor cores
+    float evict_max = -INFINITY;
+    for (int l = lane; l < 2 * n_split; l += 32)
+        evict_max = fmaxf(evict_max, unorder_bits((uint32_t)(keys[(size_t)l * kCap + kKeep - 1] >> 32)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) evict_max = fmaxf(evict_max, __shfl_xor_sync(kFull, evict_max, o));
+    __syncwarp();
     for (int i = lane; i < c; i += 32) {
         unsigned long long k = keys[i];
         if ((uint32_t)(k >> 32) != kNegInfBits) {
@@ -1294,6 +1324,11 @@ merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, lon
         cand[q * top_k + i] = -1;
         if (scores) scores[q * top_k + i] = -INFINITY;
     }
+    // same proof as in scan_kernel<MODE_LISTS>: the top_k-th canonical score must beat what an evicted candidate
+    // could have reached
+    const float kth = r == top_k ? unorder_bits((uint32_t)(prev >> 32)) : -INFINITY;
+    if (lane == 0 && lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(norms, false)))
+        lfail_list[atomicAdd(lfail_count, 1)] = (int)q;
 }
 
 }  // namespace
@@ -1340,11 +1375,19 @@ int mark(fwav_ctx *ctx, int slot, int k, cudaStream_t st) {
 // exact list kernel over packed tiles (small tables, forced mode, fallback of the fast path)
 int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const float *d_q, const float *d_emb, long long n_q,
                  long long n_d, int n_stages, int top_k, const uint8_t *d_active, int32_t *d_cand, float *d_scores, int dbg,
-                 cudaStream_t st, bool compact = false) {
+                 cudaStream_t st, const unsigned *d_norms, bool compact = false) {
     ScanArgs a = {};
     a.q_tiles = d_qt; a.e_tiles = d_et; a.Q = d_q; a.E = d_emb; a.n_q = n_q; a.n_d = n_d;
     a.n_stages = n_stages; a.top_k = top_k; a.active = d_active; a.cand = d_cand; a.scores = d_scores;
     a.dbg = dbg;
+    // rows whose lists cannot prove their top_k (a boundary crowded within the filter's error) go to the FFMA kernel
+    int *d_lfail = nullptr;
+    {
+        int rc0;
+        if ((rc0 = fwav_ws_reserve(ctx, WS_UMMA_LFAIL, (size_t)(n_q + 4) * sizeof(int), (void **)&d_lfail))) return rc0;
+        FWAV_CUDA(ctx, cudaMemsetAsync(d_lfail + n_q, 0, sizeof(int), st));
+    }
+    a.lfail_list = d_lfail; a.lfail_count = d_lfail + n_q; a.norms = d_norms;
     const long long q_pairs = (n_q + kQPair - 1) / kQPair;
     // few queries: split the table between several CTA pairs per 256 queries so that the machine is full
     const long long resident = ctx->num_sms / 2;
@@ -1367,7 +1410,28 @@ int launch_lists(fwav_ctx *ctx, const uint4 *d_qt, const uint4 *d_et, const floa
     }
     if (split > 1) {
         merge_parts_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(d_q, d_emb, n_q, (int)split, top_k, d_active, a.parts,
-                                                                    d_cand, d_scores);
+                                                                    d_cand, d_scores, d_norms, a.lfail_list, a.lfail_count);
+        FWAV_LAUNCH_CHECK(ctx);
+    }
+    int n_lfail = 0;
+    FWAV_CUDA(ctx, cudaMemcpyAsync(&n_lfail, d_lfail + n_q, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FWAV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_lfail > 0 && !dbg) {
+        if (getenv("FWAV_UMMA_VERBOSE"))
+            fprintf(stderr, "[fwav] list kernel: %d of %lld rows could not prove their top_k: FFMA kernel\n", n_lfail, n_q);
+        ctx->umma_ffma_queries += n_lfail;
+        unsigned char *blk = nullptr;
+        const size_t sz_q = (((size_t)n_lfail * ED * sizeof(float)) + 255) & ~(size_t)255,
+                     sz_c = (((size_t)n_lfail * top_k * sizeof(int32_t)) + 255) & ~(size_t)255;
+        int rc1;
+        if ((rc1 = fwav_ws_reserve(ctx, WS_UMMA_PARTS, sz_q + 2 * sz_c, (void **)&blk))) return rc1;     // the parts are consumed
+        float *d_fq = reinterpret_cast<float *>(blk);
+        int32_t *d_fc = reinterpret_cast<int32_t *>(blk + sz_q);
+        float *d_fs = reinterpret_cast<float *>(blk + sz_q + sz_c);
+        gather_rows_kernel<<<(n_lfail * (ED / 4) + 255) / 256, 256, 0, st>>>(d_q, d_lfail, n_lfail, d_fq);
+        FWAV_LAUNCH_CHECK(ctx);
+        if ((rc1 = fwav_launch_topk_ffma(ctx, d_fq, n_lfail, d_emb, n_d, ED, top_k, nullptr, d_fc, d_fs, st))) return rc1;
+        scatter_cand_kernel<<<(n_lfail * top_k + 255) / 256, 256, 0, st>>>(d_fc, d_fs, d_lfail, n_lfail, top_k, d_cand, d_scores);
         FWAV_LAUNCH_CHECK(ctx);
     }
     return FWAV_OK;
@@ -1438,6 +1502,14 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             fprintf(stderr, "[fwav] live embedding dimensions %04x (%s): %s split\n", live, known ? "known" : "unknown",
                     compact ? "compact (2 MMAs per stage)" : "plain");
     }
+    // largest row norms of both tables: the error bounds of the filter scores scale with them (score_slack)
+    unsigned *d_norms = nullptr;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_NORMS, 4 * sizeof(unsigned), (void **)&d_norms))) return rc;
+    FWAV_CUDA(ctx, cudaMemsetAsync(d_norms, 0, 2 * sizeof(unsigned), st));
+    row_norm2_max_kernel<<<grid_for(ctx, n_q), 256, 0, st>>>(d_q, n_q, d_norms);
+    FWAV_LAUNCH_CHECK(ctx);
+    row_norm2_max_kernel<<<grid_for(ctx, n_d), 256, 0, st>>>(d_emb, n_d, d_norms + 1);
+    FWAV_LAUNCH_CHECK(ctx);
     // row-major float32 -> packed fp16 tiles (role 0: queries, 1: domains; stride > 1: the sample table of pass 1)
     auto pack = [&](const float *src, long long rows, long long tiles, uint4 *dst, int stride, int role) -> int {
         if (compact)
@@ -1461,7 +1533,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if (!fast) {
         for (int k = 1; k <= 4; ++k)
             if ((rc = mark(ctx, 0, k, st))) return rc;
-        if ((rc = launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st, compact)))
+        if ((rc = launch_lists(ctx, d_qt, d_et, d_q, d_emb, n_q, n_d, (int)n_stages, top_k, d_active, d_cand, d_scores, dbg, st, d_norms, compact)))
             return rc;
         if ((rc = mark(ctx, 0, 5, st))) return rc;
         ctx->search_slots_used = 1;
@@ -1497,13 +1569,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 8) * sizeof(float), (void **)&d_theta))) return rc;
     float *d_theta_hi = d_theta + n_q;
     int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
-    // largest row norms of both tables: the error bounds of the filter passes scale with them (score_slack)
-    unsigned *d_norms = reinterpret_cast<unsigned *>(d_theta + 2 * n_q + 4);
-    FWAV_CUDA(ctx, cudaMemsetAsync(d_norms, 0, 2 * sizeof(unsigned), st));
-    row_norm2_max_kernel<<<grid_for(ctx, n_q), 256, 0, st>>>(d_q, n_q, d_norms);
-    FWAV_LAUNCH_CHECK(ctx);
-    row_norm2_max_kernel<<<grid_for(ctx, n_d), 256, 0, st>>>(d_emb, n_d, d_norms + 1);
-    FWAV_LAUNCH_CHECK(ctx);
+
     int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
     if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
         const int v = atoi(cap_env);
@@ -1734,7 +1800,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                             d_in_t = d_fqt2;
                         }
                         rc = launch_lists(ctx, d_in_t, d_et, d_in, d_emb, n_fail2, n_d, (int)n_stages, top_k, nullptr,
-                                          d_list2 ? d_fc2 : d_fc, d_list2 ? d_fs2 : d_fs, dbg, st, compact);
+                                          d_list2 ? d_fc2 : d_fc, d_list2 ? d_fs2 : d_fs, dbg, st, d_norms, compact);
                     } else {
                         rc = fwav_launch_topk_ffma(ctx, d_in, n_fail2, d_emb, n_d, ED, top_k, nullptr, d_list2 ? d_fc2 : d_fc,
                                                    d_list2 ? d_fs2 : d_fs, st);

@@ -60,6 +60,9 @@ SIGNATURES = [
     ("fwav_decode_iter_gated", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int,
                                          C.c_double, C.c_double, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     ("fwav_decode_converge", C.c_int, [c_ctx, c_ptr, C.c_int, C.c_double, c_ptr, c_ptr]),
+    ("fwav_decode_iter_bcast", C.c_int, [c_ctx, c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, i64, C.c_int,
+                                         C.c_double, C.c_double, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         C.POINTER(c_ptr), C.c_int, C.c_int, i64, c_ptr]),
     ("fwav_compress_device", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, i64, C.c_int, C.c_int, C.c_int,
                                        C.c_double, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -382,6 +385,14 @@ class Context:
         self._check(self.lib.fwav_decode_iter_gated(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
                                                     float(s_clip), float(s_damping), int(bool(first)), d_cur, d_next,
                                                     d_sums, d_state, stream))
+
+    def decode_iter_bcast(self, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size, s_clip, s_damping,
+                          first, d_cur, d_next, d_sums, d_state, targets, multimem, target_offset, stream=None):
+        arr = (c_ptr * len(targets))(*[int(t) for t in targets])
+        self._check(self.lib.fwav_decode_iter_bcast(self.h, d_domains, n_d, d_idx, d_s, d_o, d_sym, n_r, range_size,
+                                                    float(s_clip), float(s_damping), int(bool(first)), d_cur, d_next,
+                                                    d_sums, d_state, arr, len(targets), int(bool(multimem)),
+                                                    int(target_offset), stream))
 
     def decode_converge(self, d_sums_all, n_parts, eps, d_state, stream=None):
         self._check(self.lib.fwav_decode_converge(self.h, d_sums_all, int(n_parts), float(eps), d_state, stream))

@@ -29,6 +29,8 @@ built from the oracle:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -97,13 +99,18 @@ def compress_sharded(engine, signal, ranges, tile_size, emb_dim=16, top_k=32, en
 
 
 def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, convergence_eps=1e-3,
-                   s_clip=16.0, s_damping=0.0, gather_every_iteration=True):
+                   s_clip=16.0, s_damping=0.0, gather_every_iteration=True, fused=None):
     """Every rank passes the FULL match arrays; returns (recon tensor of n_ranges*range_size on every rank,
     iterations run, last delta).
 
     No host read-back inside the loop: per iteration the ranks all-gather their two float64 sums, a one-thread
     kernel adds them in rank order and takes the convergence decision into a device-side state, and the iteration
-    kernels that follow a `done` return at once.  The state is read once, after the last launch."""
+    kernels that follow a `done` return at once.  The state is read once, after the last launch.
+
+    `fused` (default: when the engine offers it and the reconstruction is exchanged every iteration): the iteration
+    kernel itself stores every output sample into the full buffer of every GPU -- one multimem.st to the NVSwitch
+    multicast address of a symmetric allocation, or plain stores through peer pointers -- so the exchange the north
+    star asks for overlaps the compute and no all-gather of the reconstruction is issued at all."""
     import torch
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -115,25 +122,37 @@ def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, co
     bufs = [engine.empty((cap * N,), torch.float32), engine.empty((cap * N,), torch.float32)]
     for b in bufs:
         b.zero_()
-    full = engine.empty((world * cap * N,), torch.float32) if world > 1 else None
+    sym_full = None
+    if world > 1 and gather_every_iteration and fused is not False and hasattr(engine, "symmetric_full") and \
+            N in (4, 8, 16, 32) and (cap * N) % 4 == 0:
+        sym_full = engine.symmetric_full(world * cap * N)           # None when symmetric memory is not available
+    if fused and sym_full is None:
+        raise RuntimeError("fused decode asked for, but the engine has no symmetric memory for the full buffer")
+    full = sym_full[0] if sym_full else (engine.empty((world * cap * N,), torch.float32) if world > 1 else None)
     all_sums = engine.empty((world * 2,), torch.float64)
     state = engine.new_state()
     for it in range(iterations):
         # iteration `it` reads bufs[it & 1] and writes bufs[(it + 1) & 1]
-        sums = engine.decode_iter(domains, idx[lo:hi], s[lo:hi], o[lo:hi], sym[lo:hi], N, s_clip, s_damping,
-                                  it == 0, bufs[it & 1], bufs[(it + 1) & 1], state)
+        if sym_full:
+            sums = engine.decode_iter_bcast(domains, idx[lo:hi], s[lo:hi], o[lo:hi], sym[lo:hi], N, s_clip, s_damping,
+                                            it == 0, bufs[it & 1], bufs[(it + 1) & 1], state, sym_full, rank * cap * N)
+        else:
+            sums = engine.decode_iter(domains, idx[lo:hi], s[lo:hi], o[lo:hi], sym[lo:hi], N, s_clip, s_damping,
+                                      it == 0, bufs[it & 1], bufs[(it + 1) & 1], state)
         if world > 1:
             dist.all_gather_into_tensor(all_sums, sums)
         else:
             all_sums.copy_(sums)
         engine.converge(all_sums, world, convergence_eps, state)        # rank order: bit-stable for a given world size
-        if world > 1 and gather_every_iteration:
+        if world > 1 and gather_every_iteration and not sym_full:
             dist.all_gather_into_tensor(full, bufs[(it + 1) & 1])
     it_run, delta = engine.read_state(state)                            # the one synchronisation of the decode
     cur = bufs[it_run & 1]
     if world == 1:
         return cur[:n_r * N], it_run, delta
-    if not gather_every_iteration or it_run < iterations or it_run == 0:
+    if sym_full and it_run > 0:
+        engine.symmetric_barrier(sym_full)           # every rank's last stores have landed in every full buffer
+    elif not gather_every_iteration or it_run < iterations or it_run == 0:
         dist.all_gather_into_tensor(full, cur)       # converged early: the gathers after it carried the stale buffer
     full = full.view(world, cap * N)
     out = torch.cat([full[r, :(b - a) * N] for r, (a, b) in enumerate(bounds)])
@@ -216,6 +235,37 @@ class CudaEngine:
         self.ctx.decode_iter_gated(domains.data_ptr(), domains.shape[0], idx.data_ptr(), s.data_ptr(), o.data_ptr(),
                                    sym.data_ptr(), idx.shape[0], N, s_clip, s_damping, first, cur.data_ptr(),
                                    nxt.data_ptr(), self._sums.data_ptr(), state.data_ptr(), self._stream())
+        return self._sums
+
+    def symmetric_full(self, numel):
+        """Full reconstruction buffer in symmetric memory (same allocation on every rank, peer-mapped; NVSwitch
+        multicast address when the fabric offers one).  Returns (tensor, targets, multimem, handle) or None."""
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(numel, dtype=self.torch.float32, device=self.device)
+            hdl = symm.rendezvous(t, dist.group.WORLD)
+            want_mc = os.environ.get("FWAV_DECODE_MULTIMEM", "1") != "0"
+            if want_mc and hdl.has_multicast_support() and hdl.multicast_ptr:
+                return t, [int(hdl.multicast_ptr)], True, hdl
+            return t, [int(p) for p in hdl.buffer_ptrs], False, hdl
+        except Exception as e:                       # no NVLink peer access / old torch: the NCCL all-gather path
+            import logging
+            logging.getLogger("fwavc").warning("symmetric memory unavailable (%s): decode falls back to NCCL all-gather", e)
+            return None
+
+    def symmetric_barrier(self, sym_full):
+        sym_full[3].barrier(channel=0)
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def decode_iter_bcast(self, domains, idx, s, o, sym, N, s_clip, s_damping, first, cur, nxt, state, sym_full, offset):
+        if self._sums is None:
+            self._sums = self.empty((2,), self.torch.float64)
+        _, targets, multimem, _ = sym_full
+        self.ctx.decode_iter_bcast(domains.data_ptr(), domains.shape[0], idx.data_ptr(), s.data_ptr(), o.data_ptr(),
+                                   sym.data_ptr(), idx.shape[0], N, s_clip, s_damping, first, cur.data_ptr(),
+                                   nxt.data_ptr(), self._sums.data_ptr(), state.data_ptr(), targets, multimem, offset,
+                                   self._stream())
         return self._sums
 
     def converge(self, all_sums, parts, eps, state):

@@ -620,14 +620,15 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
     out["c3"] = info
     idx, s, o, sym, err, dom = res
     dec = {}
-    for tag, every in (("allgather_every_iteration", True), ("allgather_once", False)):
+    for tag, every, fused in (("fused_store_every_iteration", True, None), ("allgather_every_iteration", True, False),
+                              ("allgather_once", False, False)):
         ms = []
         for rep in range(2):
             sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             rec, it, delta = D.decode_sharded(eng, dom, idx, s, o, sym, N, iterations=32, convergence_eps=0.0,
-                                              s_damping=0.5, gather_every_iteration=every)
+                                              s_damping=0.5, gather_every_iteration=every, fused=fused)
             e1.record()
             torch.cuda.synchronize()
             if rep:
@@ -752,14 +753,16 @@ def run_decode_sharded(torch, dist, dev, local, peaks, args):
     eng = D.CudaEngine(local)
     iters = 32
     res = {}
-    for tag, every in (("allgather_every_iteration", True), ("allgather_once", False)):
+    for tag, every, fused in (("fused_store_every_iteration", True, None), ("allgather_every_iteration", True, False),
+                              ("allgather_once", False, False)):
         ms = []
         for rep in range(3):
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out, it, delta = D.decode_sharded(eng, domains, idx, s, o, sym, N, iterations=iters,
-                                              convergence_eps=0.0, s_damping=0.5, gather_every_iteration=every)
+                                              convergence_eps=0.0, s_damping=0.5, gather_every_iteration=every,
+                                              fused=fused)
             e1.record()
             torch.cuda.synchronize()
             if rep:

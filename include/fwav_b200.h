@@ -172,6 +172,19 @@ int fwav_decode_iter_gated(fwav_ctx *ctx, const float *d_domains, int64_t n_doma
                            fwav_decode_state *d_state, void *stream);
 int fwav_decode_converge(fwav_ctx *ctx, const double *d_sums_all, int n_parts, double convergence_eps,
                          fwav_decode_state *d_state, void *stream);
+/* fwav_decode_iter_gated fused with the exchange the north star asks for ("the reconstruction buffer is all-gathered
+ * over NVLink each iteration"): besides d_next, every output sample is stored at element target_offset + i of the FULL
+ * reconstruction buffer of every GPU, from inside the kernel.  `targets` is a HOST array of n_targets device addresses
+ * of that buffer: with multimem != 0 exactly one, the NVSwitch multicast address of a symmetric allocation (one
+ * multimem.st per 16 bytes, replicated by the switch); otherwise one peer-mapped pointer per GPU (plain stores over
+ * NVLink).  No collective follows the kernel; the caller synchronises the ranks once before reading the full
+ * buffers.  range_size 4, 8, 16 or 32. */
+int fwav_decode_iter_bcast(fwav_ctx *ctx, const float *d_domains, int64_t n_domains,
+                           const int32_t *d_idx, const float *d_s, const float *d_o, const uint8_t *d_sym,
+                           int64_t n_ranges, int range_size, double s_clip, double s_damping, int first,
+                           const float *d_cur, float *d_next, double *d_sums, fwav_decode_state *d_state,
+                           void *const *targets, int n_targets, int multimem, int64_t target_offset,
+                           void *stream);
 
 /* Device pipeline A1..A7 on resident inputs: replaces the process/queue
  * pipeline of compress_audio (fractal.py:1114-1245) between "ranges framed"
