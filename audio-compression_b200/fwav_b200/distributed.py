@@ -128,6 +128,8 @@ def decode_sharded(engine, domains, idx, s, o, sym, range_size, iterations=8, co
         sym_full = engine.symmetric_full(world * cap * N)           # None when symmetric memory is not available
     if fused and sym_full is None:
         raise RuntimeError("fused decode asked for, but the engine has no symmetric memory for the full buffer")
+    if sym_full:
+        engine.symmetric_barrier(sym_full)           # nobody still reads the buffer of a previous decode
     full = sym_full[0] if sym_full else (engine.empty((world * cap * N,), torch.float32) if world > 1 else None)
     all_sums = engine.empty((world * 2,), torch.float64)
     state = engine.new_state()
@@ -240,19 +242,29 @@ class CudaEngine:
     def symmetric_full(self, numel):
         """Full reconstruction buffer in symmetric memory (same allocation on every rank, peer-mapped; NVSwitch
         multicast address when the fabric offers one).  Returns (tensor, targets, multimem, handle) or None."""
+        want_mc = os.environ.get("FWAV_DECODE_MULTIMEM", "1") != "0"
+        cache = self.__dict__.setdefault("_symm", {})
+        if (numel, want_mc) in cache:                # allocation + rendezvous are collective and slow: once per size
+            return cache[(numel, want_mc)]
         try:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
-            t = symm.empty(numel, dtype=self.torch.float32, device=self.device)
-            hdl = symm.rendezvous(t, dist.group.WORLD)
-            want_mc = os.environ.get("FWAV_DECODE_MULTIMEM", "1") != "0"
-            if want_mc and hdl.has_multicast_support() and hdl.multicast_ptr:
-                return t, [int(hdl.multicast_ptr)], True, hdl
-            return t, [int(p) for p in hdl.buffer_ptrs], False, hdl
+            key = ("buf", numel)
+            if key not in cache:
+                t = symm.empty(numel, dtype=self.torch.float32, device=self.device)
+                cache[key] = (t, symm.rendezvous(t, dist.group.WORLD))
+            t, hdl = cache[key]
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if want_mc and mc:
+                res = (t, [mc], True, hdl)
+            else:
+                res = (t, [int(p) for p in hdl.buffer_ptrs], False, hdl)
         except Exception as e:                       # no NVLink peer access / old torch: the NCCL all-gather path
             import logging
             logging.getLogger("fwavc").warning("symmetric memory unavailable (%s): decode falls back to NCCL all-gather", e)
-            return None
+            res = None
+        cache[(numel, want_mc)] = res
+        return res
 
     def symmetric_barrier(self, sym_full):
         sym_full[3].barrier(channel=0)
