@@ -127,7 +127,9 @@ struct ScanArgs {
 
 
 // UMMA instruction descriptor: D=F32, A=B=F16, both K-major, N=256, M=256 (cta_group::2)
-constexpr uint32_t idesc_for(int cg) { return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)((kQTile * cg) >> 4) << 24); }
+// (acc16: half-precision accumulators, D=F16 -- one value per 32-bit TMEM column, read two per register with
+// tcgen05.ld ...pack::16b; see the A16 variant of scan_kernel)
+constexpr uint32_t idesc_for(int cg, bool acc16 = false) { return ((acc16 ? 0u : 1u) << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)((kQTile * cg) >> 4) << 24); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -213,9 +215,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
            (1ull << 46) | (6ull << 61);
 }
 // D[tmem] (+)= A[smem] . B[smem]^T, fp16 operands, K = 16, f32 accumulate; CG == 2: M = 256 over the CTA pair
-template <int CG>
+template <int CG, bool A16 = false>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    if (CG == 2)
+    if (A16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc_for(1, true)), "r"(accumulate)
+            : "memory");
+    else if (CG == 2)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -258,6 +267,65 @@ __device__ __forceinline__ void tmem_wait_ld1(uint32_t (&a)[32]) {
 }
 __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&a)[32], uint32_t (&b)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a), FWAV_RW32(b)::"memory");
+}
+
+// 32 lanes x 64 columns of half-precision accumulators -> 32 registers per thread, two adjacent columns per register
+// (column 2j in the low half of register j, column 2j + 1 in the high half)
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : FWAV_R32(v)
+        : "r"(taddr)
+        : "memory");
+}
+// Per-half signed 16-bit maximum of three packed registers (DPX, SASS VIMNMX3.S16x2).  fp16 bit patterns of
+// non-negative values order like signed 16-bit integers, and every negative value sorts below every non-negative
+// one -- all a threshold filter with a non-negative threshold needs.
+__device__ __forceinline__ unsigned pmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
+// [even-column maximum | odd-column maximum] of a packed 64-column chunk: the same 3-input tree as chunk_max
+__device__ __forceinline__ unsigned chunk_max_p(const uint32_t (&v)[32]) {
+    unsigned m[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) m[i] = pmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    m[10] = pmax3(v[30], v[31], v[31]);
+    const unsigned a = pmax3(m[0], m[1], m[2]), b = pmax3(m[3], m[4], m[5]), c = pmax3(m[6], m[7], m[8]);
+    return pmax3(pmax3(a, b, c), m[9], m[10]);
+}
+// does either half of v exceed the threshold t1 (packed twice in t1x2)?
+__device__ __forceinline__ bool p_beats(unsigned v, unsigned t1x2) { return pmax3(v, t1x2, t1x2) != t1x2; }
+// visit the columns of a packed chunk whose value exceeds t1, pruning with the max tree (cf. for_each_ge)
+template <class F>
+__device__ __forceinline__ void for_each_gt_p(const uint32_t (&v)[32], unsigned t1x2, F f) {
+    const int t1 = (int)(short)(t1x2 & 0xffffu);
+    auto leaf = [&](int r) {
+        if ((int)(short)(v[r] & 0xffffu) > t1) f(2 * r);
+        if ((int)(short)(v[r] >> 16) > t1) f(2 * r + 1);
+    };
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        unsigned m[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i] = pmax3(v[9 * g + 3 * i], v[9 * g + 3 * i + 1], v[9 * g + 3 * i + 2]);
+        if (p_beats(pmax3(m[0], m[1], m[2]), t1x2)) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (p_beats(m[i], t1x2)) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        if (p_beats(v[9 * g + 3 * i + e], t1x2)) leaf(9 * g + 3 * i + e);
+                }
+            }
+        }
+    }
+    if (p_beats(pmax3(v[27], v[28], v[29]), t1x2)) {
+#pragma unroll
+        for (int e = 27; e < 30; ++e)
+            if (p_beats(v[e], t1x2)) leaf(e);
+    }
+    if (p_beats(v[30], t1x2)) leaf(30);
+    if (p_beats(v[31], t1x2)) leaf(31);
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -348,12 +416,16 @@ row_norm2_max_kernel(const float *__restrict__ x, long long n_rows, unsigned *__
 // the chain of C:  |T1 - C| <= (2^-10 + 2^-22 + 16 * 2^-23 + 16 * 2^-24) * B + 2^-23 * (nq + ne)  =  9.796e-4 * B + ...
 //   (B = 2: 1.96e-3; measured 1.1e-3).
 // ---------------------------------------------------------------------------
-constexpr float kFullSlackPerB = 7.39e-6f, kHiSlackPerB = 9.796e-4f, kSlackPerNorm = 1.2e-7f;
+// hi*hi with HALF-PRECISION accumulators (A16): on top of the above the result is delivered as an fp16 number, 2^-10
+// relative at worst (truncation; rounding to nearest would be 2^-11), |result| <= B:  |T16 - C| <= 1.957e-3 * B + ...
+//   (B = 2: 3.9e-3; measured with scripts/umma_f16acc_probe acc: see DESIGN.md 4.3).
+constexpr float kFullSlackPerB = 7.39e-6f, kHiSlackPerB = 9.796e-4f, kA16SlackPerB = 1.957e-3f, kSlackPerNorm = 1.2e-7f;
 
 // norms: largest squared row norm of the queries [0] and of the domains [1] (row_norm2_max_kernel)
-__device__ __forceinline__ float score_slack(const unsigned *__restrict__ norms, bool hi_only) {
+// filter: 0 full split, 1 hi*hi term alone, 2 hi*hi with half-precision accumulators
+__device__ __forceinline__ float score_slack(const unsigned *__restrict__ norms, int filter) {
     const float nq = sqrtf(__uint_as_float(norms[0])) * (1.0f + 1e-6f), ne = sqrtf(__uint_as_float(norms[1])) * (1.0f + 1e-6f);
-    return (hi_only ? kHiSlackPerB : kFullSlackPerB) * nq * ne + kSlackPerNorm * (nq + ne);
+    return (filter == 2 ? kA16SlackPerB : filter == 1 ? kHiSlackPerB : kFullSlackPerB) * nq * ne + kSlackPerNorm * (nq + ne);
 }
 
 // ---------------------------------------------------------------------------
@@ -595,9 +667,16 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
 #define FWAV_ALT_SETS 1
 #endif
 
-template <int MODE, bool HI, int CG, bool COMPACT = false>
+// A16 (collect pass, hi*hi-only, single CTAs): HALF-PRECISION ACCUMULATORS.  The ALU pipe is what bounds the collect
+// pass (every score through a 3-input max at half rate); f16 accumulators come out of TMEM two per register
+// (tcgen05.ld ...pack::16b) and the DPX packed maximum (VIMNMX3.S16x2) handles both halves in one instruction: half
+// the registers, half the ALU work per score, and a warp's whole 128-column share of a stage fits one round of loads,
+// so the accumulator goes back before anything is reduced.  The price is the filter's error: the result is rounded
+// to fp16 (2^-10 relative at worst), see score_slack.
+template <int MODE, bool HI, int CG, bool COMPACT = false, bool A16 = false>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
     static_assert(!(HI && COMPACT), "the hi*hi-only variant reads part 0 alone: no separate compact form");
+    static_assert(!A16 || (HI && MODE == MODE_COLLECT && CG == 1 && FWAV_ALT_SETS), "half-precision accumulators: hi*hi-only collect pass");
     // hi*hi-only collect pass: the sixteen epilogue warps form two sets, one per TMEM buffer.  A set takes every
     // other stage (128 columns per warp), so while one set waits for its tcgen05.ld the other one is reducing;
     // with all warps on every stage they move in lockstep and the load time adds to the ALU time (collect pass of
@@ -762,7 +841,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
                 if (HI) {
-                    umma_f16<CG>(d, da_hi, db_hi, 0);
+                    umma_f16<CG, A16>(d, da_hi, db_hi, 0);
                 } else if (COMPACT) {
                     umma_f16<CG>(d, da_lo, db_lo, 0);      // part 1 . part 1 = hi*lo
                     umma_f16<CG>(d, da_hi, db_hi, 1);      // part 0 . part 0 = hi*hi + lo*hi
@@ -834,6 +913,46 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 const float m2 = chunk_max(v[2]), m3 = chunk_max(v[3]);
                 const unsigned hits = (m0 > tau ? 1u : 0u) | (m1 > tau ? 2u : 0u) | (m2 > tau ? 4u : 0u) | (m3 > tau ? 8u : 0u);
                 if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
+            }
+        } else if (kAlt && A16 && !(dbg & 8)) {
+            // the row's threshold in the accumulators' own format, rounded DOWN (nothing that reaches theta is lost),
+            // minus one unit so that "exceeds" means "reaches"; +inf (pruned rows) stays out of reach
+            unsigned t1x2;
+            {
+                const float t = tau > 0.0f ? tau : 0.0f;
+                const int hb = (int)__half_as_ushort(__float2half_rd(t));
+                t1x2 = (unsigned)((hb - 1) & 0xffff) * 0x10001u;
+            }
+            uint32_t x0[32], x1[32];
+            int it = 0;
+            tt = t_first + set;
+            if (tt >= s_hi) tt -= n_visit;
+            const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tempty + 8 * set;
+            for (int t = set; t < n_visit; t += 2, ++it) {
+                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+                tc_fence_after();
+                tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
+                tmem_ld32_pack16(t_lane + 64, x1);
+                tmem_wait_ld2(x0, x1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(bar_e);
+                const int col0 = tt * kDStage + colhalf * 128;
+                tt += 2;
+                if (tt >= s_hi) tt -= n_visit;
+                const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
+                if (p_beats(pmax3(m0, m1, m1), t1x2)) {
+                    if (p_beats(m0, t1x2))
+                        for_each_gt_p(x0, t1x2, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + j;
+                            ++cnt;
+                        });
+                    if (p_beats(m1, t1x2))
+                        for_each_gt_p(x1, t1x2, [&](int j) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + 64 + j;
+                            ++cnt;
+                        });
+                }
             }
         } else if (kAlt && !(dbg & 8)) {
             uint32_t x0[32], x1[32];
@@ -1043,7 +1162,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 // at most evict_max + slack canonically: unless the top_k-th canonical score beats that, a true member
                 // of the top_k may have been evicted (more than 16 candidates crowding the boundary within the filter's
                 // error) and the row goes to the FFMA kernel.
-                if (lane == 0 && a.lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(a.norms, false)))
+                if (lane == 0 && a.lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(a.norms, 0)))
                     a.lfail_list[atomicAdd(a.lfail_count, 1)] = (int)qq;
                 __syncwarp();
             }
@@ -1105,8 +1224,8 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
     }
     unsigned long long *keys = fin_keys + (size_t)warp * key_cap;
     // how far the filter's score may sit from the canonical one (score_slack): the margin of the proof below
-    const float slack = score_slack(norms, hi_only != 0);
-    const float slack_full = score_slack(norms, false);
+    const float slack = score_slack(norms, hi_only);
+    const float slack_full = score_slack(norms, 0);
     int c = 0;
     bool ok = true, overflow = false;
     for (int p = 0; p < parts; ++p) {                  // parts = 4 column groups x table splits
@@ -1232,17 +1351,22 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
 // Few: the collect pass may filter with the hi*hi term alone.  (A wrong guess costs fallbacks, never correctness.)
 __global__ void count_flat_kernel(const float *__restrict__ theta, const float *__restrict__ theta_hi, long long n_q,
                                   const unsigned *__restrict__ norms, int *__restrict__ counts) {
-    const float room = 2.0f * score_slack(norms, true);
-    int flat = 0, live = 0;
+    // counts[0]: queries without room for the hi*hi filter (twice its error bound: theta_hi is only an estimate of the
+    // top_k-th score); counts[2]: without room for the half-precision-accumulator filter (1.5 x its bound: the bound
+    // assumes truncation, and a query that lacks the room only costs a second chance); counts[1]: live queries
+    const float room = 2.0f * score_slack(norms, 1), room16 = 1.5f * score_slack(norms, 2);
+    int flat = 0, live = 0, flat16 = 0;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n_q; q += (long long)gridDim.x * blockDim.x) {
         const float t = theta[q];
         if (t == INFINITY) continue;            // pruned
         ++live;
         flat += (theta_hi[q] - t < room) ? 1 : 0;
+        flat16 += (theta_hi[q] - t < room16) ? 1 : 0;
     }
     flat = __reduce_add_sync(0xffffffffu, flat);
     live = __reduce_add_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(counts, flat); atomicAdd(counts + 1, live); }
+    flat16 = __reduce_add_sync(0xffffffffu, flat16);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(counts, flat); atomicAdd(counts + 1, live); atomicAdd(counts + 2, flat16); }
 }
 
 // fallback plumbing: the failed queries as a dense table, and their results back in place
@@ -1327,7 +1451,7 @@ merge_parts_kernel(const float *__restrict__ Q, const float *__restrict__ E, lon
     // same proof as in scan_kernel<MODE_LISTS>: the top_k-th canonical score must beat what an evicted candidate
     // could have reached
     const float kth = r == top_k ? unorder_bits((uint32_t)(prev >> 32)) : -INFINITY;
-    if (lane == 0 && lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(norms, false)))
+    if (lane == 0 && lfail_list && evict_max != -INFINITY && !(kth > evict_max + score_slack(norms, 0)))
         lfail_list[atomicAdd(lfail_count, 1)] = (int)q;
 }
 
@@ -1346,6 +1470,7 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
+constexpr bool kDefaultAcc16 = false;         // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
 inline int grid_for(const fwav_ctx *ctx, long long work) {
@@ -1354,12 +1479,12 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
 }
 
 // one launch of the scan skeleton: `groups` tensor-core groups of 128 * CG queries, each scanned by `split` of them
-template <int MODE, bool HI, int CG, bool COMPACT = false>
+template <int MODE, bool HI, int CG, bool COMPACT = false, bool A16 = false>
 int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
     constexpr int smem = (int)smem_bytes(MODE, CG);
     // function attributes are per device: set before every launch (a process may hold contexts on several GPUs)
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    scan_kernel<MODE, HI, CG, COMPACT><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    scan_kernel<MODE, HI, CG, COMPACT, A16><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1611,21 +1736,27 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                            : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
             return rc;
         // may pass 2 filter with the hi*hi term too?  Only if (nearly) every query has room for its error bound
-        bool hi_only = false;
+        bool hi_only = false, acc16 = false;
         if (!(mode_env && !strcmp(mode_env, "precise"))) {
-            FWAV_CUDA(ctx, cudaMemsetAsync(d_flat, 0, 2 * sizeof(int), st));
+            FWAV_CUDA(ctx, cudaMemsetAsync(d_flat, 0, 3 * sizeof(int), st));
             count_flat_kernel<<<grid_for(ctx, nq), 256, 0, st>>>(d_theta + q0, d_theta_hi + q0, nq, d_norms, d_flat);
             FWAV_LAUNCH_CHECK(ctx);
-            int h_flat[2] = {0, 0};
+            int h_flat[3] = {0, 0, 0};
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_flat, d_flat, sizeof h_flat, cudaMemcpyDeviceToHost, st));
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
             // (a query without that room is not lost: it fails verification and takes the second chance below,
             // which is cheap next to the +35 % of a full-split pass)
             hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.02 * h_flat[1];
-            if (mode_env && !strcmp(mode_env, "hionly")) hi_only = true;
+            if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
+            // half-precision accumulators on top (single CTAs only): when (nearly) every query has room for that too
+            const char *a16_env = getenv("FWAV_UMMA_ACC16");
+            acc16 = hi_only && single && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
+                    (double)h_flat[2] <= 0.02 * h_flat[1];
+            if (mode_env && !strcmp(mode_env, "acc16") && single) acc16 = true;
+            if (mode_env && !strcmp(mode_env, "hionly")) acc16 = false;
             if (getenv("FWAV_UMMA_VERBOSE"))
-                fprintf(stderr, "[fwav] search batch at %lld: %d of %d live queries leave less than twice the hi*hi error bound between their top_k-th score and theta: %s collect pass\n",
-                        q0, h_flat[0], h_flat[1], hi_only ? "hi*hi-only" : "full-split");
+                fprintf(stderr, "[fwav] search batch at %lld: of %d live queries %d lack the room for the hi*hi filter and %d for half-precision accumulators: %s collect pass\n",
+                        q0, h_flat[1], h_flat[0], h_flat[2], acc16 ? "hi*hi-only, fp16 accumulators" : hi_only ? "hi*hi-only" : "full-split");
         }
         ctx->search_hi_only = hi_only;
         if ((rc = mark(ctx, slot, 2, st))) return rc;
@@ -1669,6 +1800,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
             if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
+            else if (acc16)
+                rc = launch_scan<MODE_COLLECT, true, 1, false, true>(ctx, ax, g, sp, st);
             else if (hi_only)
                 rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);
             else
@@ -1701,7 +1834,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             finalize_kernel<<<(unsigned)((ax.n_q + kFinWarps - 1) / kFinWarps), kFinWarps * 32,
                               fin_smem, st>>>(
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
-                d_norms, hi_only ? 1 : 0, d_cand + (q0 + qoff) * top_k,
+                d_norms, acc16 ? 2 : hi_only ? 1 : 0, d_cand + (q0 + qoff) * top_k,
                 d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
                 d_theta + q0 + qoff, key_cap);
             FWAV_LAUNCH_CHECK(ctx);
@@ -1749,7 +1882,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 if (rs > 16) rs = 16;
                 if (rs > n_stages / 8) rs = n_stages / 8;
                 if (rs < 1) rs = 1;
-                const bool retry = single && (hi_only || rs >= 2) && !(mode_env && !strcmp(mode_env, "noretry"));
+                // (rs == 1 with a full-split first pass still pays: boundary cases -- the bulk of the failures on crowded
+                // scores, 2 % of config 4's queries -- only need their threshold lowered, not more room; without the
+                // second pass they would all go to the FFMA kernel: 477 ms per million queries of the config-4 shape)
+                const bool retry = single && !(mode_env && !strcmp(mode_env, "noretry"));
                 int n_fail2 = n_fail;
                 const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
                 if (retry) {

@@ -8,7 +8,7 @@ import json
 d=json.loads(open('gpurun_out/r02i_c4.json').read().strip().splitlines()[-1])
 print(d['ms_per_step'], d['roofline'].get('search_phases_ms'))
 PY
-FWAV_UMMA_COMPACT=0 FWAV_UMMA_VERBOSE=1 timeout 600 python bench.py --workload c4 --scale 0.1 --steps 1 --warmup 1 --no-decode --no-cpu > $O/r02i_c4_nc.json 2> $O/r02i_c4_nc.err
+true
 grep "fwav\]" $O/r02i_c4_nc.err | tail -6 | cut -c1-260
 python - <<'PY'
 import json

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -120,7 +121,72 @@ __global__ void max3_h2_probe(const uint32_t *in, uint32_t *out) {
     out[0] = d;
 }
 
+// "acc" command (round 2): how far is a half-precision accumulator from the exact dot product?  Random two-unit-head
+// rows (what the embeddings are), rounded to fp16 first (so only the tensor core's own arithmetic is measured), many
+// launches; also checks what tcgen05.ld ...pack::16b returns against the plain dump.
+static int accuracy(int n_launch) {
+    static __half hA[128 * 16], hB[256 * 16];
+    static uint32_t hD[128 * 256], hP[128 * 256];
+    __half *dA, *dB;
+    uint32_t *dD;
+    long long *dC;
+    cudaMalloc(&dA, sizeof hA); cudaMalloc(&dB, sizeof hB); cudaMalloc(&dD, 128 * 256 * 4); cudaMalloc(&dC, 8);
+    double max_err = 0, max_ulp = 0, sum_err = 0;
+    long long n = 0, n_pack_bad = 0, n_near = 0;
+    double max_err_near = 0;
+    unsigned long long st = 88172645463325252ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    auto gauss = [&]() { double u = rnd() + 1e-12, v = rnd(); return sqrt(-2 * log(u)) * cos(6.283185307179586 * v); };
+    for (int l = 0; l < n_launch; ++l) {
+        auto fill = [&](__half *dst, int rows) {
+            for (int r = 0; r < rows; ++r) {
+                double x[16], n0 = 0, n1 = 0;
+                for (int k = 0; k < 16; ++k) { x[k] = gauss(); (k < 8 ? n0 : n1) += x[k] * x[k]; }
+                // every fourth launch: rows that point the same way (scores near 2, where an fp16 ulp is largest)
+                for (int k = 0; k < 16; ++k) {
+                    double v = x[k] / sqrt(k < 8 ? n0 : n1);
+                    if (l % 4 == 3) v = 0.97 * (k % 8 == 0 ? 1.0 : 0.05) + 0.03 * v;
+                    dst[r * 16 + k] = __float2half((float)v);
+                }
+            }
+        };
+        fill(hA, 128); fill(hB, 256);
+        cudaMemcpy(dA, hA, sizeof hA, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, hB, sizeof hB, cudaMemcpyHostToDevice);
+        for (int mode : {0, 2}) {
+            probe_kernel<<<1, 160, 4096 + 8192 + 64>>>(dA, dB, dD, dC, mode, 1);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed\n"); return 1; }
+            cudaMemcpy(mode ? hP : hD, dD, sizeof hD, cudaMemcpyDeviceToHost);
+        }
+        for (int r = 0; r < 128; ++r)
+            for (int c = 0; c < 256; ++c) {
+                double ex = 0;
+                for (int k = 0; k < 16; ++k) ex += (double)__half2float(hA[r * 16 + k]) * (double)__half2float(hB[c * 16 + k]);
+                __half_raw h; h.x = hD[r * 256 + c] & 0xffff;
+                const double got = __half2float(__half(h));
+                const double err = fabs(got - ex), ulp = ldexp(1.0, (int)floor(log2(fmax(fabs(ex), 6.1e-5))) - 10);
+                if (err > max_err) max_err = err;
+                if (err / ulp > max_ulp) max_ulp = err / ulp;
+                if (fabs(ex) > 1.0) { ++n_near; if (err > max_err_near) max_err_near = err; }
+                sum_err += err; ++n;
+                // pack::16b dump: the probe loads at column bases 0, 32, 64 ...; the load at base c0 returns, in register j,
+                // columns c0 + 2j (low half) and c0 + 2j + 1 (high half)
+                const int c0 = (c / 32) * 32, j = c % 32;
+                if (c0 + 2 * j + 1 < 256) {
+                    const uint32_t pk = hP[r * 256 + c0 + j];
+                    const uint32_t lo = hD[r * 256 + c0 + 2 * j] & 0xffff, hi = hD[r * 256 + c0 + 2 * j + 1] & 0xffff;
+                    if (pk != (lo | hi << 16)) ++n_pack_bad;
+                }
+            }
+    }
+    printf("{\"probe\": \"f16 accumulator accuracy\", \"scores\": %lld, \"max_abs_err\": %.3e, \"max_err_in_fp16_ulps_of_the_result\": %.3f, "
+           "\"mean_abs_err\": %.3e, \"scores_above_1\": %lld, \"max_abs_err_above_1\": %.3e, \"pack16b_mismatches\": %lld}\n",
+           n, max_err, max_ulp, sum_err / n, n_near, max_err_near, n_pack_bad);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && !strcmp(argv[1], "acc")) return accuracy(argc > 2 ? atoi(argv[2]) : 100);
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const int n_rep = argc > 2 ? atoi(argv[2]) : 1;
     __half hA[128 * 16], hB[256 * 16];
