@@ -1182,6 +1182,208 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 }
 
 // ---------------------------------------------------------------------------
+// collect_hi_kernel: the hi*hi-only collect pass (the dominant kernel) with FOUR issuing threads (round 2).
+//
+// Measured on B200 with the epilogue switched off (debug build, FWAV_UMMA_DEBUG=8): two issuer threads put one
+// M128 N256 K16 instruction per ~300 cycles on the tensor pipe -- 38 ms for config 2, although the instruction itself
+// takes 171.  One issue is a serial chain in its thread (the "operands landed" wait, ~90 cycles even when long
+// complete; the "accumulator free" wait; the instruction, which blocks its thread until the pipe takes it; two
+// commits): ~600 cycles.  So the collect pass was bound by how fast two threads can issue, whatever the epilogue does.
+// Here four threads issue, round-robin over the stages (thread i: stages t = i (mod 4), accumulator t & 1), and each
+// thread is also the producer of its own stages' operands (bulk copies one own-stage ahead), so that the CTA stays at
+// 20 warps -- five per scheduler, what 96 registers allow.  Two threads now take turns on one accumulator; a parity
+// wait of the one that runs ahead would pass on the phase BEFORE the one it needs, so every (accumulator, thread)
+// pair has its own "free" barrier and the epilogue arrives on the one of the thread that issues the NEXT use.
+// Epilogue: the two-set layout of scan_kernel (set = accumulator, 128 columns per warp), with float32 accumulators
+// (two rounds of two 32-column loads) or -- A16 -- half-precision ones (one round of two packed loads, DPX packed max).
+// Same inputs, outputs and candidate-buffer layout as scan_kernel<MODE_COLLECT, true, 1>.
+// ---------------------------------------------------------------------------
+constexpr int kHiIss = 4;
+constexpr int kHiThreads = (16 + kHiIss) * 32;
+constexpr uint32_t kHiOffBars = kPartBytes;                       // after the hi part of the query tile
+constexpr uint32_t kHiOffRing = 8192;                             // 1024-aligned
+constexpr uint32_t kHiStageBytes = 2 * kPartBytes;                // the two hi tiles of a 256-domain stage
+constexpr uint32_t kHiSmem = kHiOffRing + kStages * kHiStageBytes;
+
+template <bool A16>
+__global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_q = a.n_q;
+    const uint8_t *__restrict__ active = a.active;
+    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
+    const long long q_base = (long long)group_id * kQTile;
+    const uint32_t bars = smem_u32(smem + kHiOffBars);
+    // barrier slots (8 bytes each): full[8] empty[8] tfull[2] tfree[2][2] a
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_tfull = bars + 16 * kStages,
+                   bar_tfree = bar_tfull + 16, bar_a = bar_tfree + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kHiOffBars + 16 * kStages + 64);
+
+    {   // energy-pruned stretch: nothing to scan
+        int any = 0;
+        for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
+            const long long q = q_base + i;
+            if (q < n_q && (!active || active[q])) any = 1;
+        }
+        if (!__syncthreads_or(any)) {
+            for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
+                const long long q = q_base + i;
+                if (q < n_q)
+                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) mbar_init(bar_tfull + 8 * b, 1);
+        for (int b = 0; b < 4; ++b) mbar_init(bar_tfree + 8 * b, 8);          // the eight epilogue warps of a set
+        mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
+    const int n_visit = s_hi - s_lo;
+    const int t_first = s_lo + (int)((q_base / kDStage) % n_visit);
+
+    if (warp >= 16) {
+        // ===== issuer + producer threads: thread i owns the stages t = i (mod 4) and their ring slots i, i + 4 =====
+        if (lane == 0) {
+            const int i = warp - 16, b = i & 1, j = i >> 1;
+            auto load_stage = [&](int t) {             // the two hi tiles of the t-th stage this CTA visits
+                int tt = t_first + t;
+                if (tt >= s_hi) tt -= n_visit;
+                const int s = t & (kStages - 1);
+                const uint32_t dst = smem_u32(smem + kHiOffRing + s * kHiStageBytes);
+                const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
+                mbar_expect_tx(bar_full + 8 * s, 2 * kPartBytes);
+                bulk_g2s(dst, t0, kPartBytes, bar_full + 8 * s);
+                bulk_g2s(dst + kPartBytes, t1, kPartBytes, bar_full + 8 * s);
+            };
+            if (i == 0) {
+                mbar_expect_tx(bar_a, kPartBytes);
+                bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kPartBytes, bar_a);
+            }
+            if (i < n_visit) load_stage(i);
+            mbar_wait(bar_a, 0);
+            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
+            const uint32_t d = tmem_base + (uint32_t)(b * kDStage);
+            int k = 0;
+            for (int t = i; t < n_visit; t += kHiIss, ++k) {
+                const int tn = t + kHiIss;
+                if (tn < n_visit) {                    // next own stage: its slot was freed by this thread's own MMA of t - 4
+                    mbar_wait(bar_empty + 8 * (tn & (kStages - 1)), (uint32_t)(((tn / kStages) & 1) ^ 1));
+                    load_stage(tn);
+                }
+                const int s = t & (kStages - 1);
+                const uint64_t db_hi = smem_desc(smem_u32(smem + kHiOffRing + s * kHiStageBytes));
+                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kStages) & 1));
+                // use u = t >> 1 = 2 k + j of accumulator b: its previous use has been read (nothing to wait for at u = 0)
+                if (j == 1 || k > 0) mbar_wait(bar_tfree + 8 * (2 * b + j), (uint32_t)((j == 1 ? k : k - 1) & 1));
+                tc_fence_after();
+                umma_f16<1, A16>(d, da_hi, db_hi, 0);
+                umma_commit<1>(bar_tfull + 8 * b);
+                umma_commit<1>(bar_empty + 8 * s);
+            }
+        }
+    } else {
+        // ===== epilogue: one query row per thread; warp = (TMEM lane quadrant, set = accumulator, column half) =====
+        const int quad = warp & 3, half = warp >> 2, set = half & 1, colhalf = half >> 1;
+        const long long q = q_base + quad * 32 + lane;
+        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
+        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + half) * (long long)a.cap;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kDStage + colhalf * 128);
+        const uint32_t bar_f = bar_tfull + 8 * set;
+        int cnt = 0;
+        int tt = t_first + set;
+        if (tt >= s_hi) tt -= n_visit;
+        uint32_t x0[32], x1[32];
+        if (A16) {
+            // the row's threshold in the accumulators' own format, rounded DOWN (nothing that reaches theta is lost),
+            // minus one unit so that "exceeds" means "reaches"; +inf (pruned rows) stays out of reach
+            const float tpos = tau > 0.0f ? tau : 0.0f;
+            const unsigned t1x2 = (unsigned)(((int)__half_as_ushort(__float2half_rd(tpos)) - 1) & 0xffff) * 0x10001u;
+            int it = 0;
+            for (int t = set; t < n_visit; t += 2, ++it) {
+                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+                tc_fence_after();
+                tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
+                tmem_ld32_pack16(t_lane + 64, x1);
+                tmem_wait_ld2(x0, x1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the thread that issues the next use
+                const int col0 = tt * kDStage + colhalf * 128;
+                tt += 2;
+                if (tt >= s_hi) tt -= n_visit;
+                const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
+                if (p_beats(pmax3(m0, m1, m1), t1x2)) {
+                    if (p_beats(m0, t1x2))
+                        for_each_gt_p(x0, t1x2, [&](int jj) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + jj;
+                            ++cnt;
+                        });
+                    if (p_beats(m1, t1x2))
+                        for_each_gt_p(x1, t1x2, [&](int jj) {
+                            if (cnt < a.cap) cbuf[cnt] = col0 + 64 + jj;
+                            ++cnt;
+                        });
+                }
+            }
+        } else {
+            auto look = [&](const uint32_t (&x)[32], float m, int col) {
+                if (m >= tau)
+                    for_each_ge(x, tau, [&](int jj) {
+                        if (cnt < a.cap) cbuf[cnt] = col + jj;
+                        ++cnt;
+                    });
+            };
+            int it = 0;
+            for (int t = set; t < n_visit; t += 2, ++it) {
+                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+                tc_fence_after();
+                tmem_ld32(t_lane, x0);
+                tmem_ld32(t_lane + 32, x1);
+                tmem_wait_ld2(x0, x1);
+                const int col0 = tt * kDStage + colhalf * 128;
+                tt += 2;
+                if (tt >= s_hi) tt -= n_visit;
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0);
+                    look(x1, mb, col0 + 32);
+                }
+                tmem_ld32(t_lane + 64, x0);
+                tmem_ld32(t_lane + 96, x1);
+                tmem_wait_ld2(x0, x1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));
+                {
+                    const float ma = chunk_max(x0), mb = chunk_max(x1);
+                    look(x0, ma, col0 + 64);
+                    look(x1, mb, col0 + 96);
+                }
+            }
+        }
+        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Pass 3 of the fast path: one warp per query.  Every collected candidate is
 // re-scored with the canonical float32 chain, the best top_k are selected
 // best-first (score descending, index ascending) and the result is VERIFIED:
@@ -1470,6 +1672,7 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
+constexpr int kDefaultIssuers = 2;            // issuing threads of the hi*hi-only collect pass (FWAV_UMMA_ISSUERS)
 constexpr bool kDefaultAcc16 = false;         // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
@@ -1485,6 +1688,15 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
     // function attributes are per device: set before every launch (a process may hold contexts on several GPUs)
     FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     scan_kernel<MODE, HI, CG, COMPACT, A16><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
+// the four-issuer hi*hi-only collect pass: one CTA per 128 queries and table share
+template <bool A16>
+int launch_collect_hi(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_hi_kernel<A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHiSmem));
+    collect_hi_kernel<A16><<<(unsigned)(groups * split), kHiThreads, kHiSmem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1759,6 +1971,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         q0, h_flat[1], h_flat[0], h_flat[2], acc16 ? "hi*hi-only, fp16 accumulators" : hi_only ? "hi*hi-only" : "full-split");
         }
         ctx->search_hi_only = hi_only;
+        const char *iss_env = getenv("FWAV_UMMA_ISSUERS");         // 4: collect_hi_kernel, 2: scan_kernel (hi*hi-only batches)
+        const bool iss4 = iss_env ? atoi(iss_env) == 4 : kDefaultIssuers == 4;
         if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {
@@ -1800,6 +2014,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
             if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
+            else if (hi_only && single && iss4 && !dbg)
+                rc = acc16 ? launch_collect_hi<true>(ctx, ax, g, sp, st) : launch_collect_hi<false>(ctx, ax, g, sp, st);
             else if (acc16)
                 rc = launch_scan<MODE_COLLECT, true, 1, false, true>(ctx, ax, g, sp, st);
             else if (hi_only)
