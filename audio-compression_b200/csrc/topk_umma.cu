@@ -1384,6 +1384,158 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
 }
 
 // ---------------------------------------------------------------------------
+// collect_q_kernel: the same pass with FOUR 128-column half-precision accumulators, one epilogue warp per (TMEM lane
+// quadrant, accumulator) and one issuer/producer thread per accumulator.
+// A tile is 128 domains (M128 N128 K16); tile t goes into accumulator t & 3, issued by thread t & 3 and read by the
+// four warps (one per lane quadrant) of set t & 3.  With half-precision accumulators a warp's whole share of a tile --
+// 128 columns -- is two packed loads (64 registers), so the accumulator goes back after ONE round of loads, and every
+// accumulator has its own issuing thread and its own set of warps: nothing is shared between the four chains but the
+// tensor pipe and the ALU.  Each issuer owns four slots of a 16-tile ring and loads three own tiles ahead.
+// ---------------------------------------------------------------------------
+constexpr int kQRing = 16;                                        // 128-domain hi tiles in flight (4 KB each)
+constexpr uint32_t kQOffBars = kPartBytes, kQOffRing = 8192;
+constexpr uint32_t kQSmem = kQOffRing + kQRing * kPartBytes;
+
+__global__ void __launch_bounds__(kHiThreads, 1) collect_q_kernel(const ScanArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_q = a.n_q;
+    const uint8_t *__restrict__ active = a.active;
+    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
+    const long long q_base = (long long)group_id * kQTile;
+    const uint32_t bars = smem_u32(smem + kQOffBars);
+    // barrier slots (8 bytes each): full[16] empty[16] tfull[4] tfree[4] a
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQRing, bar_tfull = bars + 16 * kQRing,
+                   bar_tfree = bar_tfull + 32, bar_a = bar_tfree + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQOffBars + 16 * kQRing + 80);
+    {   // energy-pruned stretch: nothing to scan
+        int any = 0;
+        for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
+            const long long q = q_base + i;
+            if (q < n_q && (!active || active[q])) any = 1;
+        }
+        if (!__syncthreads_or(any)) {
+            for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
+                const long long q = q_base + i;
+                if (q < n_q)
+                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+            }
+            return;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kQRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tfree + 8 * b, 4); }
+        mbar_init(bar_a, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
+    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;          // in 128-domain tiles
+    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
+    constexpr uint32_t kIdesc = ((uint32_t)(kDTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);   // D=F16, A=B=F16, N=128, M=128
+
+    if (warp >= 16) {
+        // ===== issuer + producer threads: thread i owns the tiles t = i (mod 4), accumulator i, ring slots i, i+4, i+8, i+12 =====
+        if (lane == 0) {
+            const int i = warp - 16;
+            auto load_tile = [&](int t) {
+                int tt = t_first + t;
+                if (tt >= t_hi) tt -= n_visit;
+                const int s = t & (kQRing - 1);
+                mbar_expect_tx(bar_full + 8 * s, kPartBytes);
+                bulk_g2s(smem_u32(smem + kQOffRing + s * kPartBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kPartBytes,
+                         bar_full + 8 * s);
+            };
+            if (i == 0) {
+                mbar_expect_tx(bar_a, kPartBytes);
+                bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kPartBytes, bar_a);
+            }
+            for (int t = i; t < n_visit && t < i + 12; t += 4) load_tile(t);          // three own tiles ahead
+            mbar_wait(bar_a, 0);
+            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
+            const uint32_t d = tmem_base + (uint32_t)(i * kDTile);
+            int k = 0;
+            for (int t = i; t < n_visit; t += 4, ++k) {
+                const int tn = t + 12;
+                if (tn < n_visit) {                    // its slot was freed by this thread's own MMA of t - 4
+                    mbar_wait(bar_empty + 8 * (tn & (kQRing - 1)), (uint32_t)(((tn / kQRing) & 1) ^ 1));
+                    load_tile(tn);
+                }
+                const int s = t & (kQRing - 1);
+                const uint64_t db_hi = smem_desc(smem_u32(smem + kQOffRing + s * kPartBytes));
+                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQRing) & 1));
+                mbar_wait(bar_tfree + 8 * i, (uint32_t)((k & 1) ^ 1));        // the k-th use of this thread's accumulator
+                tc_fence_after();
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(d), "l"(da_hi), "l"(db_hi), "r"(kIdesc), "r"(0)
+                    : "memory");
+                umma_commit<1>(bar_tfull + 8 * i);
+                umma_commit<1>(bar_empty + 8 * s);
+            }
+        }
+    } else {
+        // ===== epilogue: one query row per thread; warp = (TMEM lane quadrant, set = accumulator) =====
+        const int quad = warp & 3, set = warp >> 2;
+        const long long q = q_base + quad * 32 + lane;
+        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
+        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + set) * (long long)a.cap;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kDTile);
+        const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tfree + 8 * set;
+        const float tpos = tau > 0.0f ? tau : 0.0f;
+        const unsigned t1x2 = (unsigned)(((int)__half_as_ushort(__float2half_rd(tpos)) - 1) & 0xffff) * 0x10001u;
+        int cnt = 0;
+        int tt = t_first + set;
+        if (tt >= t_hi) tt -= n_visit;
+        uint32_t x0[32], x1[32];
+        int it = 0;
+        for (int t = set; t < n_visit; t += 4, ++it) {
+            mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+            tc_fence_after();
+            tmem_ld32_pack16(t_lane, x0);            // all 128 columns of the tile, in one round
+            tmem_ld32_pack16(t_lane + 64, x1);
+            tmem_wait_ld2(x0, x1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(bar_e);
+            const int col0 = tt * kDTile;
+            tt += 4;
+            if (tt >= t_hi) tt -= n_visit;
+            const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
+            if (p_beats(pmax3(m0, m1, m1), t1x2)) {
+                if (p_beats(m0, t1x2))
+                    for_each_gt_p(x0, t1x2, [&](int jj) {
+                        if (cnt < a.cap) cbuf[cnt] = col0 + jj;
+                        ++cnt;
+                    });
+                if (p_beats(m1, t1x2))
+                    for_each_gt_p(x1, t1x2, [&](int jj) {
+                        if (cnt < a.cap) cbuf[cnt] = col0 + 64 + jj;
+                        ++cnt;
+                    });
+            }
+        }
+        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + set] = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Pass 3 of the fast path: one warp per query.  Every collected candidate is
 // re-scored with the canonical float32 chain, the best top_k are selected
 // best-first (score descending, index ascending) and the result is VERIFIED:
@@ -1701,6 +1853,13 @@ int launch_collect_hi(fwav_ctx *ctx, const ScanArgs &a, long long groups, long l
     return FWAV_OK;
 }
 
+int launch_collect_q(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmem));
+    collect_q_kernel<<<(unsigned)(groups * split), kHiThreads, kQSmem, st>>>(a);
+    FWAV_LAUNCH_CHECK(ctx);
+    return FWAV_OK;
+}
+
 // record phase boundary k of timed batch `slot` (events are created on first use)
 int mark(fwav_ctx *ctx, int slot, int k, cudaStream_t st) {
     if (slot >= fwav_ctx::kSearchSlots) return FWAV_OK;
@@ -1973,6 +2132,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         ctx->search_hi_only = hi_only;
         const char *iss_env = getenv("FWAV_UMMA_ISSUERS");         // 4: collect_hi_kernel, 2: scan_kernel (hi*hi-only batches)
         const bool iss4 = iss_env ? atoi(iss_env) == 4 : kDefaultIssuers == 4;
+        const bool quadq = iss_env && atoi(iss_env) == 44;          // collect_q_kernel: four accumulators, four issuers
         if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {
@@ -2014,6 +2174,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
             if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
+            else if (acc16 && single && quadq && !dbg)
+                rc = launch_collect_q(ctx, ax, g, sp, st);
             else if (hi_only && single && iss4 && !dbg)
                 rc = acc16 ? launch_collect_hi<true>(ctx, ax, g, sp, st) : launch_collect_hi<false>(ctx, ax, g, sp, st);
             else if (acc16)
