@@ -128,7 +128,7 @@ struct ScanArgs {
 
 // UMMA instruction descriptor: D=F32, A=B=F16, both K-major, N=256, M=256 (cta_group::2)
 // (acc16: half-precision accumulators, D=F16 -- one value per 32-bit TMEM column, read two per register with
-// tcgen05.ld ...pack::16b; see the A16 variant of scan_kernel)
+// tcgen05.ld ...pack::16b; see collect_hi_kernel)
 constexpr uint32_t idesc_for(int cg, bool acc16 = false) { return ((acc16 ? 0u : 1u) << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kDStage >> 3) << 17) | ((uint32_t)((kQTile * cg) >> 4) << 24); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -667,16 +667,9 @@ constexpr int kTraceFrom = 256, kTraceStages = 64;
 #define FWAV_ALT_SETS 1
 #endif
 
-// A16 (collect pass, hi*hi-only, single CTAs): HALF-PRECISION ACCUMULATORS.  The ALU pipe is what bounds the collect
-// pass (every score through a 3-input max at half rate); f16 accumulators come out of TMEM two per register
-// (tcgen05.ld ...pack::16b) and the DPX packed maximum (VIMNMX3.S16x2) handles both halves in one instruction: half
-// the registers, half the ALU work per score, and a warp's whole 128-column share of a stage fits one round of loads,
-// so the accumulator goes back before anything is reduced.  The price is the filter's error: the result is rounded
-// to fp16 (2^-10 relative at worst), see score_slack.
-template <int MODE, bool HI, int CG, bool COMPACT = false, bool A16 = false>
+template <int MODE, bool HI, int CG, bool COMPACT = false>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1) scan_kernel(const ScanArgs a) {
     static_assert(!(HI && COMPACT), "the hi*hi-only variant reads part 0 alone: no separate compact form");
-    static_assert(!A16 || (HI && MODE == MODE_COLLECT && CG == 1 && FWAV_ALT_SETS), "half-precision accumulators: hi*hi-only collect pass");
     // hi*hi-only collect pass: the sixteen epilogue warps form two sets, one per TMEM buffer.  A set takes every
     // other stage (128 columns per warp), so while one set waits for its tcgen05.ld the other one is reducing;
     // with all warps on every stage they move in lockstep and the load time adds to the ALU time (collect pass of
@@ -841,7 +834,7 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 tc_fence_after();
                 // small cross terms first, the hi*hi term last; one K=16 instruction each
                 if (HI) {
-                    umma_f16<CG, A16>(d, da_hi, db_hi, 0);
+                    umma_f16<CG>(d, da_hi, db_hi, 0);
                 } else if (COMPACT) {
                     umma_f16<CG>(d, da_lo, db_lo, 0);      // part 1 . part 1 = hi*lo
                     umma_f16<CG>(d, da_hi, db_hi, 1);      // part 0 . part 0 = hi*hi + lo*hi
@@ -913,46 +906,6 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 const float m2 = chunk_max(v[2]), m3 = chunk_max(v[3]);
                 const unsigned hits = (m0 > tau ? 1u : 0u) | (m1 > tau ? 2u : 0u) | (m2 > tau ? 4u : 0u) | (m3 > tau ? 8u : 0u);
                 if (__any_sync(kFull, hits != 0)) absorb_stage(v, hits, tau, base, n_d, lists, scratch, lane);
-            }
-        } else if (kAlt && A16 && !(dbg & 8)) {
-            // the row's threshold in the accumulators' own format, rounded DOWN (nothing that reaches theta is lost),
-            // minus one unit so that "exceeds" means "reaches"; +inf (pruned rows) stays out of reach
-            unsigned t1x2;
-            {
-                const float t = tau > 0.0f ? tau : 0.0f;
-                const int hb = (int)__half_as_ushort(__float2half_rd(t));
-                t1x2 = (unsigned)((hb - 1) & 0xffff) * 0x10001u;
-            }
-            uint32_t x0[32], x1[32];
-            int it = 0;
-            tt = t_first + set;
-            if (tt >= s_hi) tt -= n_visit;
-            const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tempty + 8 * set;
-            for (int t = set; t < n_visit; t += 2, ++it) {
-                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
-                tc_fence_after();
-                tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
-                tmem_ld32_pack16(t_lane + 64, x1);
-                tmem_wait_ld2(x0, x1);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(bar_e);
-                const int col0 = tt * kDStage + colhalf * 128;
-                tt += 2;
-                if (tt >= s_hi) tt -= n_visit;
-                const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
-                if (p_beats(pmax3(m0, m1, m1), t1x2)) {
-                    if (p_beats(m0, t1x2))
-                        for_each_gt_p(x0, t1x2, [&](int j) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + j;
-                            ++cnt;
-                        });
-                    if (p_beats(m1, t1x2))
-                        for_each_gt_p(x1, t1x2, [&](int j) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + 64 + j;
-                            ++cnt;
-                        });
-                }
             }
         } else if (kAlt && !(dbg & 8)) {
             uint32_t x0[32], x1[32];
@@ -1182,21 +1135,28 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 }
 
 // ---------------------------------------------------------------------------
-// collect_hi_kernel: the hi*hi-only collect pass (the dominant kernel) with FOUR issuing threads (round 2).
+// collect_hi_kernel (round 2): the hi*hi-only collect pass -- the dominant kernel -- with HALF-PRECISION ACCUMULATORS
+// and FOUR issuing threads.
 //
-// Measured on B200 with the epilogue switched off (debug build, FWAV_UMMA_DEBUG=8): two issuer threads put one
-// M128 N256 K16 instruction per ~300 cycles on the tensor pipe -- 38 ms for config 2, although the instruction itself
-// takes 171.  One issue is a serial chain in its thread (the "operands landed" wait, ~90 cycles even when long
-// complete; the "accumulator free" wait; the instruction, which blocks its thread until the pipe takes it; two
-// commits): ~600 cycles.  So the collect pass was bound by how fast two threads can issue, whatever the epilogue does.
-// Here four threads issue, round-robin over the stages (thread i: stages t = i (mod 4), accumulator t & 1), and each
-// thread is also the producer of its own stages' operands (bulk copies one own-stage ahead), so that the CTA stays at
-// 20 warps -- five per scheduler, what 96 registers allow.  Two threads now take turns on one accumulator; a parity
-// wait of the one that runs ahead would pass on the phase BEFORE the one it needs, so every (accumulator, thread)
-// pair has its own "free" barrier and the epilogue arrives on the one of the thread that issues the NEXT use.
-// Epilogue: the two-set layout of scan_kernel (set = accumulator, 128 columns per warp), with float32 accumulators
-// (two rounds of two 32-column loads) or -- A16 -- half-precision ones (one round of two packed loads, DPX packed max).
-// Same inputs, outputs and candidate-buffer layout as scan_kernel<MODE_COLLECT, true, 1>.
+// (1) Every score of the pass goes through a 3-input max on the half-rate ALU pipe.  Half-precision accumulators
+// (kind::f16 with D=F16: one value per 32-bit TMEM column) come out of TMEM two per register with
+// tcgen05.ld ...pack::16b, and the DPX packed maximum (SASS VIMNMX3.S16x2; fp16 bit patterns of non-negative values
+// order like signed 16-bit integers) handles both halves in one instruction: half the registers and half the ALU work
+// per score, and a warp's whole 128-column share of a stage fits ONE round of loads, so the accumulator goes back
+// before anything is reduced.  The price is the filter's error -- the result is delivered as an fp16 number -- which
+// score_slack accounts for (measured: scripts/umma_f16acc_probe.cu acc); batches whose queries lack the room for it
+// keep float32 accumulators (scan_kernel).
+// (2) Measured with the epilogue switched off (debug build, FWAV_UMMA_DEBUG=8): two issuer threads put one M128 N256
+// K16 instruction per ~300 cycles on the tensor pipe (38 ms for config 2) although the instruction takes 171: one
+// issue is a serial chain in its thread (the "operands landed" wait, ~90 cycles even when long complete; the
+// "accumulator free" wait; the instruction, which blocks its thread until the pipe takes it; two commits).  Here four
+// threads issue, round-robin over the stages (thread i: stages t = i (mod 4), accumulator t & 1), and each is also the
+// producer of its own stages' operands (bulk copies one own stage ahead), so the CTA stays at 20 warps -- five per
+// scheduler, what 96 registers allow.  Two threads take turns on one accumulator; a parity wait of the one that runs
+// ahead would pass on the phase BEFORE the one it needs, so every (accumulator, thread) pair has its own "free" barrier
+// and the epilogue arrives on the one of the thread that issues the NEXT use.
+// Epilogue layout, inputs, outputs and candidate buffers as scan_kernel<MODE_COLLECT, true, 1> (set = accumulator,
+// 128 columns per warp).  Config 2 on B200: 68.4 -> 60-62 ms (profiles/r02_collect_acc16_timings.txt).
 // ---------------------------------------------------------------------------
 constexpr int kHiIss = 4;
 constexpr int kHiThreads = (16 + kHiIss) * 32;
@@ -1205,7 +1165,6 @@ constexpr uint32_t kHiOffRing = 8192;                             // 1024-aligne
 constexpr uint32_t kHiStageBytes = 2 * kPartBytes;                // the two hi tiles of a 256-domain stage
 constexpr uint32_t kHiSmem = kHiOffRing + kStages * kHiStageBytes;
 
-template <bool A16>
 __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1288,7 +1247,7 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
                 // use u = t >> 1 = 2 k + j of accumulator b: its previous use has been read (nothing to wait for at u = 0)
                 if (j == 1 || k > 0) mbar_wait(bar_tfree + 8 * (2 * b + j), (uint32_t)((j == 1 ? k : k - 1) & 1));
                 tc_fence_after();
-                umma_f16<1, A16>(d, da_hi, db_hi, 0);
+                umma_f16<1, true>(d, da_hi, db_hi, 0);
                 umma_commit<1>(bar_tfull + 8 * b);
                 umma_commit<1>(bar_empty + 8 * s);
             }
@@ -1305,212 +1264,23 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         int tt = t_first + set;
         if (tt >= s_hi) tt -= n_visit;
         uint32_t x0[32], x1[32];
-        if (A16) {
-            // the row's threshold in the accumulators' own format, rounded DOWN (nothing that reaches theta is lost),
-            // minus one unit so that "exceeds" means "reaches"; +inf (pruned rows) stays out of reach
-            const float tpos = tau > 0.0f ? tau : 0.0f;
-            const unsigned t1x2 = (unsigned)(((int)__half_as_ushort(__float2half_rd(tpos)) - 1) & 0xffff) * 0x10001u;
-            int it = 0;
-            for (int t = set; t < n_visit; t += 2, ++it) {
-                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
-                tc_fence_after();
-                tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
-                tmem_ld32_pack16(t_lane + 64, x1);
-                tmem_wait_ld2(x0, x1);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the thread that issues the next use
-                const int col0 = tt * kDStage + colhalf * 128;
-                tt += 2;
-                if (tt >= s_hi) tt -= n_visit;
-                const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
-                if (p_beats(pmax3(m0, m1, m1), t1x2)) {
-                    if (p_beats(m0, t1x2))
-                        for_each_gt_p(x0, t1x2, [&](int jj) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + jj;
-                            ++cnt;
-                        });
-                    if (p_beats(m1, t1x2))
-                        for_each_gt_p(x1, t1x2, [&](int jj) {
-                            if (cnt < a.cap) cbuf[cnt] = col0 + 64 + jj;
-                            ++cnt;
-                        });
-                }
-            }
-        } else {
-            auto look = [&](const uint32_t (&x)[32], float m, int col) {
-                if (m >= tau)
-                    for_each_ge(x, tau, [&](int jj) {
-                        if (cnt < a.cap) cbuf[cnt] = col + jj;
-                        ++cnt;
-                    });
-            };
-            int it = 0;
-            for (int t = set; t < n_visit; t += 2, ++it) {
-                mbar_wait_hot(bar_f, (uint32_t)(it & 1));
-                tc_fence_after();
-                tmem_ld32(t_lane, x0);
-                tmem_ld32(t_lane + 32, x1);
-                tmem_wait_ld2(x0, x1);
-                const int col0 = tt * kDStage + colhalf * 128;
-                tt += 2;
-                if (tt >= s_hi) tt -= n_visit;
-                {
-                    const float ma = chunk_max(x0), mb = chunk_max(x1);
-                    look(x0, ma, col0);
-                    look(x1, mb, col0 + 32);
-                }
-                tmem_ld32(t_lane + 64, x0);
-                tmem_ld32(t_lane + 96, x1);
-                tmem_wait_ld2(x0, x1);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));
-                {
-                    const float ma = chunk_max(x0), mb = chunk_max(x1);
-                    look(x0, ma, col0 + 64);
-                    look(x1, mb, col0 + 96);
-                }
-            }
-        }
-        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 16) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------
-// collect_q_kernel: the same pass with FOUR 128-column half-precision accumulators, one epilogue warp per (TMEM lane
-// quadrant, accumulator) and one issuer/producer thread per accumulator.
-// A tile is 128 domains (M128 N128 K16); tile t goes into accumulator t & 3, issued by thread t & 3 and read by the
-// four warps (one per lane quadrant) of set t & 3.  With half-precision accumulators a warp's whole share of a tile --
-// 128 columns -- is two packed loads (64 registers), so the accumulator goes back after ONE round of loads, and every
-// accumulator has its own issuing thread and its own set of warps: nothing is shared between the four chains but the
-// tensor pipe and the ALU.  Each issuer owns four slots of a 16-tile ring and loads three own tiles ahead.
-// ---------------------------------------------------------------------------
-constexpr int kQRing = 16;                                        // 128-domain hi tiles in flight (4 KB each)
-constexpr uint32_t kQOffBars = kPartBytes, kQOffRing = 8192;
-constexpr uint32_t kQSmem = kQOffRing + kQRing * kPartBytes;
-
-__global__ void __launch_bounds__(kHiThreads, 1) collect_q_kernel(const ScanArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_q = a.n_q;
-    const uint8_t *__restrict__ active = a.active;
-    const int group_id = (int)blockIdx.x / a.n_split, split = (int)blockIdx.x % a.n_split;
-    const long long q_base = (long long)group_id * kQTile;
-    const uint32_t bars = smem_u32(smem + kQOffBars);
-    // barrier slots (8 bytes each): full[16] empty[16] tfull[4] tfree[4] a
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kQRing, bar_tfull = bars + 16 * kQRing,
-                   bar_tfree = bar_tfull + 32, bar_a = bar_tfree + 32;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kQOffBars + 16 * kQRing + 80);
-    {   // energy-pruned stretch: nothing to scan
-        int any = 0;
-        for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
-            const long long q = q_base + i;
-            if (q < n_q && (!active || active[q])) any = 1;
-        }
-        if (!__syncthreads_or(any)) {
-            for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
-                const long long q = q_base + i;
-                if (q < n_q)
-                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
-            }
-            return;
-        }
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kQRing; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 4; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tfree + 8 * b, 4); }
-        mbar_init(bar_a, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 16) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
-    const int t_lo = 2 * s_lo, t_hi = 2 * s_hi, n_visit = t_hi - t_lo;          // in 128-domain tiles
-    const int t_first = t_lo + (int)((q_base / kDTile) % n_visit);
-    constexpr uint32_t kIdesc = ((uint32_t)(kDTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);   // D=F16, A=B=F16, N=128, M=128
-
-    if (warp >= 16) {
-        // ===== issuer + producer threads: thread i owns the tiles t = i (mod 4), accumulator i, ring slots i, i+4, i+8, i+12 =====
-        if (lane == 0) {
-            const int i = warp - 16;
-            auto load_tile = [&](int t) {
-                int tt = t_first + t;
-                if (tt >= t_hi) tt -= n_visit;
-                const int s = t & (kQRing - 1);
-                mbar_expect_tx(bar_full + 8 * s, kPartBytes);
-                bulk_g2s(smem_u32(smem + kQOffRing + s * kPartBytes), a.e_tiles + (long long)tt * (kTileBytes / 16), kPartBytes,
-                         bar_full + 8 * s);
-            };
-            if (i == 0) {
-                mbar_expect_tx(bar_a, kPartBytes);
-                bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kPartBytes, bar_a);
-            }
-            for (int t = i; t < n_visit && t < i + 12; t += 4) load_tile(t);          // three own tiles ahead
-            mbar_wait(bar_a, 0);
-            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
-            const uint32_t d = tmem_base + (uint32_t)(i * kDTile);
-            int k = 0;
-            for (int t = i; t < n_visit; t += 4, ++k) {
-                const int tn = t + 12;
-                if (tn < n_visit) {                    // its slot was freed by this thread's own MMA of t - 4
-                    mbar_wait(bar_empty + 8 * (tn & (kQRing - 1)), (uint32_t)(((tn / kQRing) & 1) ^ 1));
-                    load_tile(tn);
-                }
-                const int s = t & (kQRing - 1);
-                const uint64_t db_hi = smem_desc(smem_u32(smem + kQOffRing + s * kPartBytes));
-                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kQRing) & 1));
-                mbar_wait(bar_tfree + 8 * i, (uint32_t)((k & 1) ^ 1));        // the k-th use of this thread's accumulator
-                tc_fence_after();
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                    ::"r"(d), "l"(da_hi), "l"(db_hi), "r"(kIdesc), "r"(0)
-                    : "memory");
-                umma_commit<1>(bar_tfull + 8 * i);
-                umma_commit<1>(bar_empty + 8 * s);
-            }
-        }
-    } else {
-        // ===== epilogue: one query row per thread; warp = (TMEM lane quadrant, set = accumulator) =====
-        const int quad = warp & 3, set = warp >> 2;
-        const long long q = q_base + quad * 32 + lane;
-        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
-        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + set) * (long long)a.cap;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kDTile);
-        const uint32_t bar_f = bar_tfull + 8 * set, bar_e = bar_tfree + 8 * set;
+        // the row's threshold in the accumulators' own format, rounded DOWN (nothing that reaches theta is lost),
+        // minus one unit so that "exceeds" means "reaches"; +inf (pruned rows) stays out of reach
         const float tpos = tau > 0.0f ? tau : 0.0f;
         const unsigned t1x2 = (unsigned)(((int)__half_as_ushort(__float2half_rd(tpos)) - 1) & 0xffff) * 0x10001u;
-        int cnt = 0;
-        int tt = t_first + set;
-        if (tt >= t_hi) tt -= n_visit;
-        uint32_t x0[32], x1[32];
         int it = 0;
-        for (int t = set; t < n_visit; t += 4, ++it) {
+        for (int t = set; t < n_visit; t += 2, ++it) {
             mbar_wait_hot(bar_f, (uint32_t)(it & 1));
             tc_fence_after();
-            tmem_ld32_pack16(t_lane, x0);            // all 128 columns of the tile, in one round
+            tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
             tmem_ld32_pack16(t_lane + 64, x1);
             tmem_wait_ld2(x0, x1);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_local(bar_e);
-            const int col0 = tt * kDTile;
-            tt += 4;
-            if (tt >= t_hi) tt -= n_visit;
+            if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the thread that issues the next use
+            const int col0 = tt * kDStage + colhalf * 128;
+            tt += 2;
+            if (tt >= s_hi) tt -= n_visit;
             const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
             if (p_beats(pmax3(m0, m1, m1), t1x2)) {
                 if (p_beats(m0, t1x2))
@@ -1525,7 +1295,7 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_q_kernel(const ScanArgs
                     });
             }
         }
-        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + set] = cnt;
+        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -1824,8 +1594,7 @@ constexpr int kCollectCap = 256;              // candidate indices kept per (que
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
-constexpr int kDefaultIssuers = 2;            // issuing threads of the hi*hi-only collect pass (FWAV_UMMA_ISSUERS)
-constexpr bool kDefaultAcc16 = false;         // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16)
+constexpr bool kDefaultAcc16 = true;          // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16=0: off)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
 inline int grid_for(const fwav_ctx *ctx, long long work) {
@@ -1834,28 +1603,20 @@ inline int grid_for(const fwav_ctx *ctx, long long work) {
 }
 
 // one launch of the scan skeleton: `groups` tensor-core groups of 128 * CG queries, each scanned by `split` of them
-template <int MODE, bool HI, int CG, bool COMPACT = false, bool A16 = false>
+template <int MODE, bool HI, int CG, bool COMPACT = false>
 int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
     constexpr int smem = (int)smem_bytes(MODE, CG);
     // function attributes are per device: set before every launch (a process may hold contexts on several GPUs)
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT, A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    scan_kernel<MODE, HI, CG, COMPACT, A16><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<MODE, HI, CG, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    scan_kernel<MODE, HI, CG, COMPACT><<<(unsigned)(CG * groups * split), n_threads(MODE), smem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
 
 // the four-issuer hi*hi-only collect pass: one CTA per 128 queries and table share
-template <bool A16>
 int launch_collect_hi(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_hi_kernel<A16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHiSmem));
-    collect_hi_kernel<A16><<<(unsigned)(groups * split), kHiThreads, kHiSmem, st>>>(a);
-    FWAV_LAUNCH_CHECK(ctx);
-    return FWAV_OK;
-}
-
-int launch_collect_q(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQSmem));
-    collect_q_kernel<<<(unsigned)(groups * split), kHiThreads, kQSmem, st>>>(a);
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHiSmem));
+    collect_hi_kernel<<<(unsigned)(groups * split), kHiThreads, kHiSmem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -2121,18 +1882,15 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
             // half-precision accumulators on top (single CTAs only): when (nearly) every query has room for that too
             const char *a16_env = getenv("FWAV_UMMA_ACC16");
-            acc16 = hi_only && single && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
+            acc16 = hi_only && single && !dbg && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
                     (double)h_flat[2] <= 0.02 * h_flat[1];
-            if (mode_env && !strcmp(mode_env, "acc16") && single) acc16 = true;
+            if (mode_env && !strcmp(mode_env, "acc16") && single && !dbg) acc16 = true;
             if (mode_env && !strcmp(mode_env, "hionly")) acc16 = false;
             if (getenv("FWAV_UMMA_VERBOSE"))
                 fprintf(stderr, "[fwav] search batch at %lld: of %d live queries %d lack the room for the hi*hi filter and %d for half-precision accumulators: %s collect pass\n",
                         q0, h_flat[1], h_flat[0], h_flat[2], acc16 ? "hi*hi-only, fp16 accumulators" : hi_only ? "hi*hi-only" : "full-split");
         }
         ctx->search_hi_only = hi_only;
-        const char *iss_env = getenv("FWAV_UMMA_ISSUERS");         // 4: collect_hi_kernel, 2: scan_kernel (hi*hi-only batches)
-        const bool iss4 = iss_env ? atoi(iss_env) == 4 : kDefaultIssuers == 4;
-        const bool quadq = iss_env && atoi(iss_env) == 44;          // collect_q_kernel: four accumulators, four issuers
         if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {
@@ -2174,12 +1932,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             const long long g = part ? tail_groups : main_groups, sp = part ? tail_split : 1;
             if (compact && !hi_only)
                 rc = launch_scan<MODE_COLLECT, false, 1, true>(ctx, ax, g, sp, st);
-            else if (acc16 && single && quadq && !dbg)
-                rc = launch_collect_q(ctx, ax, g, sp, st);
-            else if (hi_only && single && iss4 && !dbg)
-                rc = acc16 ? launch_collect_hi<true>(ctx, ax, g, sp, st) : launch_collect_hi<false>(ctx, ax, g, sp, st);
             else if (acc16)
-                rc = launch_scan<MODE_COLLECT, true, 1, false, true>(ctx, ax, g, sp, st);
+                rc = launch_collect_hi(ctx, ax, g, sp, st);
             else if (hi_only)
                 rc = single ? launch_scan<MODE_COLLECT, true, 1>(ctx, ax, g, sp, st) : launch_scan<MODE_COLLECT, true, 2>(ctx, ax, g, sp, st);
             else

@@ -540,12 +540,13 @@ def test_search_paths_agree(ctx, monkeypatch):
 
 @pytest.mark.parametrize("n_q,top_k,frac_active,mode", [(1, 1, 1.0, None), (129, 7, 1.0, None), (777, 32, 0.5, None),
                                                        (777, 32, 0.5, "precise"), (1500, 64, 0.9, None),
-                                                       (1500, 64, 0.9, "precise")])
+                                                       (1500, 64, 0.9, "precise"), (777, 32, 0.5, "hionly"),
+                                                       (777, 32, 0.5, "acc16"), (1500, 64, 0.9, "acc16")])
 def test_search_odd_shapes_random_table(ctx, monkeypatch, n_q, top_k, frac_active, mode):
     """Random unit-norm two-head embeddings, a table size that is not a multiple of anything, query counts around
-    the 128-row tile, small and large K, the collect pass on the hi*hi term alone (what the probe picks here) and
-    forced onto the full fp16 split (FWAV_UMMA_MODE=precise): the tensor-core search must equal the FFMA kernel,
-    candidates and scores."""
+    the 128-row tile, small and large K, the collect pass on the hi*hi term alone with float32 accumulators (hionly),
+    with half-precision accumulators (acc16: collect_hi_kernel) and forced onto the full fp16 split
+    (FWAV_UMMA_MODE=precise): the tensor-core search must equal the FFMA kernel, candidates and scores."""
     if mode:
         monkeypatch.setenv("FWAV_UMMA_MODE", mode)
     else:
@@ -704,8 +705,9 @@ def _music_table(ctx, seconds, seed, tile=4096, N=16, ds=4, ED=16):
     return n_d, d_emb, d_emb.to_host((n_d, ED), np.float32)
 
 
-@pytest.mark.parametrize("top_k,cap", [(32, None), (32, 48), (64, None), (64, 48)])
-def test_multi_batch_search(ctx, monkeypatch, top_k, cap):
+@pytest.mark.parametrize("top_k,cap,mode", [(32, None, None), (32, 48, None), (64, None, None), (64, 48, None),
+                                            (32, None, "hionly"), (32, 48, "acc16")])
+def test_multi_batch_search(ctx, monkeypatch, top_k, cap, mode):
     """The fast path works in batches of 2^20 queries (configs 3 and 4 run 2-21 of them per rank).  FWAV_UMMA_BATCH
     shrinks the batch so that a 5 000-query search crosses batch boundaries seven times: with a pruning mask, a split
     tail wave in every batch and (cap = 48) forced failures whose batch-local indices go through the second chance
@@ -721,6 +723,8 @@ def test_multi_batch_search(ctx, monkeypatch, top_k, cap):
     for impl in ("ffma", "umma"):
         if impl == "umma":
             monkeypatch.setenv("FWAV_UMMA_BATCH", "768")
+            if mode:
+                monkeypatch.setenv("FWAV_UMMA_MODE", mode)
             if cap:
                 monkeypatch.setenv("FWAV_UMMA_CAP", str(cap))
         set_impl(ctx, impl)
@@ -908,7 +912,7 @@ def test_forged_indices_are_rejected_not_dereferenced(ctx):
     assert np.array_equal(bits(out[:len(g["dec_default"])]), bits(g["dec_default"]))
 
 
-@pytest.mark.parametrize("top_k,mode", [(32, None), (32, "precise"), (64, None), (32, "hionly")])
+@pytest.mark.parametrize("top_k,mode", [(32, None), (32, "precise"), (64, None), (32, "hionly"), (32, "acc16"), (64, "acc16")])
 def test_search_adversarial_norms_and_near_ties(ctx, monkeypatch, top_k, mode):
     """What the error bounds of the filter passes (score_slack in topk_umma.cu) have to survive: rows far from the
     two-unit-head norm sqrt(2) the embeddings have (up to 1.6 x that), and clusters of 48 near-duplicates whose scores
