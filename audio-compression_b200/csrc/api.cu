@@ -239,6 +239,7 @@ int fwav_ctx_set_search_range_size(fwav_ctx *ctx, int range_size) {
 
 int64_t fwav_ctx_launch_count(const fwav_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx) { return ctx ? ctx->umma_fallback_queries : 0; }
+int fwav_ctx_search_route(const fwav_ctx *ctx) { return ctx ? ctx->search_route : -1; }
 int fwav_ctx_search_timings(fwav_ctx *ctx, float ms[5]) {
     if (!ctx || !ms) return FWAV_ERR_INVALID;
     FWAV_REQUIRE(ctx, ctx->search_slots_used > 0, "no tensor-core search has run on this context yet");

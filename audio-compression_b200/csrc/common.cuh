@@ -29,6 +29,7 @@ struct fwav_ctx {
     int search_slots_used = 0;
     bool search_fast_path = false;
     bool search_hi_only = false;          // last collect pass filtered with the hi*hi term alone
+    int search_route = 0;                 // last batch: 0 list kernel, 1 full split, 2 hi*hi float32 accumulators, 3 hi*hi fp16 accumulators
 
     // range_size the embedding tables of the coming searches were built for (0: unknown).  Set by the pipeline
     // entry points around their own search, or by fwav_ctx_set_search_range_size; tells the tensor-core search

@@ -1787,6 +1787,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     const char *mode_env = getenv("FWAV_UMMA_MODE");   // "lists": force the exact list kernel
     const bool fast = n_d >= kFastMinDomains && (top_k > 32 || !(mode_env && !strcmp(mode_env, "lists")));
     ctx->search_fast_path = fast;
+    ctx->search_route = 0;
     if (!fast) {
         for (int k = 1; k <= 4; ++k)
             if ((rc = mark(ctx, 0, k, st))) return rc;
@@ -1891,6 +1892,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                         q0, h_flat[1], h_flat[0], h_flat[2], acc16 ? "hi*hi-only, fp16 accumulators" : hi_only ? "hi*hi-only" : "full-split");
         }
         ctx->search_hi_only = hi_only;
+        ctx->search_route = acc16 ? 3 : hi_only ? 2 : 1;
         if ((rc = mark(ctx, slot, 2, st))) return rc;
         a.e_tiles = d_et; a.n_stages = (int)n_stages;
         if (dbg & 64) {

@@ -152,6 +152,9 @@ def compute_snr(original, reconstructed):
 
 
 # ----------------------------- file drivers (unchanged behaviour) -----------------------------
+# COMPATIBILITY TRANSLITERATION: everything from here to the end of the file restates the reference's file drivers and
+# CLI (fractal.py:1491-1669: same argparse flags and help strings, log messages, result dicts, output-path quirks)
+# because SURVEY 8(b) requires the CLI and the drivers to stay unchanged.  It is host glue, not part of the hot path.
 
 def process_file_compress(path, outdir=None, tile=1024, energy_thresh=1e-4, use_gpu=False):
     try:

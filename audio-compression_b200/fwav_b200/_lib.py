@@ -44,6 +44,7 @@ SIGNATURES = [
     ("fwav_ctx_launch_count", i64, [c_ctx]),
     ("fwav_ctx_search_fallbacks", i64, [c_ctx]),
     ("fwav_ctx_search_timings", C.c_int, [c_ctx, C.POINTER(C.c_float)]),
+    ("fwav_ctx_search_route", C.c_int, [c_ctx]),
     ("fwav_geometry", C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("fwav_count_domains", i64, [i64, C.c_int, C.c_int]),
     ("fwav_build_domains", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
@@ -241,6 +242,10 @@ class Context:
 
     def search_fallbacks(self):
         return int(self.lib.fwav_ctx_search_fallbacks(self.h))
+
+    def search_route(self):
+        """0 list kernel, 1 full split, 2 hi*hi / float32 accumulators, 3 hi*hi / fp16 accumulators (last batch)."""
+        return int(self.lib.fwav_ctx_search_route(self.h))
 
     def search_timings(self):
         """Device milliseconds of the last tensor-core search: pack, threshold pass, collect pass,

@@ -1,6 +1,9 @@
 """PCM WAV in/out with the reference's semantics (fractal.py:81-137): 8-bit
 unsigned, 16/24-bit signed and 32-bit float, multi-channel averaged to mono,
-samples returned at their integer scale (never normalised)."""
+samples returned at their integer scale (never normalised).
+
+COMPATIBILITY TRANSLITERATION of the reference's two functions (SURVEY 2 marks WAV I/O "reuse semantics verbatim",
+BASELINE.json: "read_wav_mono/write_wav ... stay unchanged"); host glue, not part of the hot path."""
 from __future__ import annotations
 
 import wave

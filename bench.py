@@ -452,7 +452,10 @@ def run_ours(args):
         peak = peaks["bf16_tflops_sustained"]
         dom_ms = search_ms["collect"] if search_ms and search_ms["collect"] > 0 else topk_ms
         fast = bool(search_ms and search_ms["collect"] > 0)
-        roof = {"kernel": "scan_kernel<MODE_COLLECT>" if fast else "scan_kernel<MODE_LISTS>",
+        route = ctx.search_route()
+        roof = {"kernel": ("collect_hi_kernel (hi*hi term, fp16 accumulators, one kind::f16 MMA per tile)" if route == 3 else
+                           "scan_kernel<MODE_COLLECT, hi*hi> (float32 accumulators, one MMA per tile)" if route == 2 else
+                           "scan_kernel<MODE_COLLECT> (full split, three MMAs per tile)" if fast else "scan_kernel<MODE_LISTS>"),
                 "bound": "tensor", "achieved": flops / (dom_ms * 1e-3) / 1e12,
                 "peak": peak, "unit": "TFLOP/s",
                 "peak_source": "sustained bf16 cuBLAS rate, " + peaks["source"] + " (= the kind::f16 instruction peak; "
@@ -460,12 +463,14 @@ def run_ours(args):
                                "profiles/r02_umma_microbench.jsonl)",
                 "search_stage_ms": topk_ms, "search_phases_ms": search_ms,
                 "achieved_whole_search_stage": flops / (topk_ms * 1e-3) / 1e12}
-        # what actually bounds a K = 16 contraction: every score leaves TMEM once (512 B/clk/SM) and goes through a
-        # 3-input max tree on the ALU pipe (17 half-rate instructions per 32 scores and scheduler)
+        # what actually bounds a K = 16 contraction: every score leaves TMEM once (512 B/clk/SM, one 32-bit column per
+        # score whatever the accumulator format) and goes through a 3-input max tree on the ALU pipe (17 half-rate
+        # instructions per 32 registers and scheduler; a register holds two scores with fp16 accumulators)
         clk = peaks["sm_max_mhz"] * 1e6
         scores = pairs / world
+        per_reg = 2.0 if route == 3 else 1.0
         roof["epilogue_floor_ms"] = {"tmem_drain": 1e3 * scores * 4.0 / (512.0 * 148 * clk),
-                                     "alu_max_tree": 1e3 * scores * (17.0 / 32.0) * 2.0 / (128.0 * 148 * clk)}
+                                     "alu_max_tree": 1e3 * scores / per_reg * (17.0 / 32.0) * 2.0 / (128.0 * 148 * clk)}
         roof["frac_of_epilogue_floor"] = max(roof["epilogue_floor_ms"].values()) / dom_ms
         topk_ms_roof = dom_ms
     else:
@@ -496,8 +501,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": config_dict(w, args.scale, world),
         "details": {"search_impl": ("tcgen05 (cta_group::1) fp16 hi/lo split: threshold pass over a strided sample "
-                                    "(M128 N256 K16, 3 MMAs/tile), collect pass (hi*hi term alone, M128 N128 K16 into four "
-                                    "accumulator buffers, when the probe after pass 1 allows it; else 3 MMAs/tile), exact "
+                                    "(M128 N256 K16, 3 MMAs/tile), collect pass (hi*hi term alone with fp16 or float32 "
+                                    "accumulators when the probe after pass 1 allows it; else 3 MMAs/tile), exact "
                                     "float32 finalize with per-query verification, second tensor-core pass then exact "
                                     "list/FFMA kernel for queries that fail it" if tensor else "FP32 FFMA"),
                     "parallelism": f"ranges sharded x{world}" + ((", tables " + ("NCCL-broadcast from rank 0" if args.bcast else "rebuilt on every rank") + ", matches all-gathered in one packed block") if world > 1 else ""),
@@ -655,9 +660,10 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
 
 def ncu_traffic(kernel):
     """DRAM bytes (read + write) per launch of the dominant kernel on config 2, from the committed
-    `ncu --set full` capture (profiles/r01_ncu_full_collect_config2_v2.json; scripts/gpu_ncu_full_collect.sh)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_collect_config2_v2.json")
-    if "COLLECT" not in kernel or not os.path.exists(path):
+    `ncu --set full` captures (profiles/r02_ncu_full_collect_*.json; scripts/r02/gpu_n.sh, gpu_e.sh)."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_collect_hi_config2.json" if "collect_hi" in kernel
+                        else "r02_ncu_full_collect_f32acc_config2.json")
+    if ("COLLECT" not in kernel and "collect_hi" not in kernel) or not os.path.exists(path):
         return None
     try:
         rec = json.load(open(path))[0]
@@ -665,10 +671,11 @@ def ncu_traffic(kernel):
         tot = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(rec[k]["value"]) * unit[rec[k]["unit"]]
-        return {"bytes_per_launch": tot, "source": "ncu --set full, profiles/r01_ncu_full_collect_config2_v2.json",
-                "note": "the packed domain table (hi parts, 63 MB) is re-streamed by every CTA and served from L2; "
-                        "DRAM sees 6.1 GB of reads (mostly sector fills under the scattered 4-byte candidate-index stores) and "
-                        "0.79 GB of writes per launch, 1.2 % of peak"}
+        return {"bytes_per_launch": tot, "source": "ncu --set full, profiles/" + os.path.basename(path),
+                "note": "the packed domain table (hi parts, 63 MB) is re-streamed by every CTA and served from L2; DRAM "
+                        "sees 6-8 GB of reads (sector fills under the scattered 4-byte candidate-index stores: staging "
+                        "them as whole sectors was measured and cost more time than it saved, DESIGN 4.3) and 0.8 GB of "
+                        "writes per launch, ~2 % of peak"}
     except Exception:
         return None
 

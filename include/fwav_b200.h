@@ -84,6 +84,11 @@ int64_t fwav_ctx_search_fallbacks(const fwav_ctx *ctx);
    ms[4] exact list kernel (small tables, or the queries the fast path handed over).  Call after the stream has been
    synchronised; returns FWAV_ERR_INVALID if no tensor-core search has run yet. */
 int fwav_ctx_search_timings(fwav_ctx *ctx, float ms[5]);
+/* Which collect pass the LAST batch of the last tensor-core search took: 0 exact list kernel (small tables), 1 full
+   fp16 hi/lo split (three instructions per tile), 2 hi*hi term alone with float32 accumulators, 3 hi*hi term alone with
+   half-precision accumulators (collect_hi_kernel).  Decided per batch from the room the queries leave for each
+   filter's error bound; results are identical either way. */
+int fwav_ctx_search_route(const fwav_ctx *ctx);
 
 /* Derived geometry of compress_audio (fractal.py:1070-1071) and the domain
  * count of build_domains_memmap (fractal.py:297-304). */
