@@ -176,6 +176,12 @@ __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
         ::"r"(bar), "r"(parity)
         : "memory");
 }
+// one lane of a converged warp (the compiler keeps warp-uniform operands of the guarded instructions in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -770,30 +776,38 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 
     if (warp == kEpi) {
         // ===== producer: bulk copies (TMA engine) of this CTA's query tile and its half of every stage =====
-        if (lane == 0) {
-            mbar_expect_tx(bar_a, kOpBytes);
-            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + ((long long)CG * pair_id + cta_rank) * (kTileBytes / 16), kOpBytes, bar_a);
+        // (the whole warp runs the loop, one elected lane issues: operands of the copy instructions stay in uniform
+        // registers instead of going through an elect-and-broadcast loop each -- see collect_hi_kernel)
+        {
+            if (elect_one()) {
+                mbar_expect_tx(bar_a, kOpBytes);
+                bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + ((long long)CG * pair_id + cta_rank) * (kTileBytes / 16), kOpBytes, bar_a);
+            }
+            __syncwarp();
             int tt = t_first;
             for (int t = 0; t < n_visit; ++t) {
                 const int s = t & (kStages - 1);
                 const uint32_t ph = (uint32_t)((t / kStages) & 1);
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 const uint32_t dst = smem_u32(smem + kOffB + s * kStageStride);
-                if (CG == 2) {
-                    // this CTA's half of the stage: its hi part, and right behind it its lo part
-                    mbar_expect_tx(bar_full + 8 * s, kOpBytes);
-                    bulk_g2s(dst, a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kOpBytes, bar_full + 8 * s);
-                } else {
-                    // both tiles of the stage: [hi 0 | hi 1] and, for the full split, [lo 0 | lo 1] behind them
-                    const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
-                    mbar_expect_tx(bar_full + 8 * s, 2 * kOpBytes);
-                    bulk_g2s(dst, t0, kPartBytes, bar_full + 8 * s);
-                    bulk_g2s(dst + kPartBytes, t1, kPartBytes, bar_full + 8 * s);
-                    if (!HI) {
-                        bulk_g2s(dst + kLoOff, t0 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
-                        bulk_g2s(dst + kLoOff + kPartBytes, t1 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
+                if (elect_one()) {
+                    if (CG == 2) {
+                        // this CTA's half of the stage: its hi part, and right behind it its lo part
+                        mbar_expect_tx(bar_full + 8 * s, kOpBytes);
+                        bulk_g2s(dst, a.e_tiles + (2ll * tt + cta_rank) * (kTileBytes / 16), kOpBytes, bar_full + 8 * s);
+                    } else {
+                        // both tiles of the stage: [hi 0 | hi 1] and, for the full split, [lo 0 | lo 1] behind them
+                        const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
+                        mbar_expect_tx(bar_full + 8 * s, 2 * kOpBytes);
+                        bulk_g2s(dst, t0, kPartBytes, bar_full + 8 * s);
+                        bulk_g2s(dst + kPartBytes, t1, kPartBytes, bar_full + 8 * s);
+                        if (!HI) {
+                            bulk_g2s(dst + kLoOff, t0 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
+                            bulk_g2s(dst + kLoOff + kPartBytes, t1 + kPartBytes / 16, kPartBytes, bar_full + 8 * s);
+                        }
                     }
                 }
+                __syncwarp();
                 if (++tt == s_hi) tt = s_lo;
             }
         }
@@ -815,11 +829,12 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
         // alternate between two threads: the first issuer warp owns the even ones (TMEM buffer 0), the second the odd
         // ones (buffer 1).  The buffers and shared-memory stages are disjoint and a commit covers
         // its own thread's MMAs, so the two instruction streams need no ordering between them.
-        if (lane == 0) {
+        // (whole warp in the loop, one elected lane issues -- as the producer above)
+        {
             mbar_wait(bar_a, 0);
             const uint32_t a_hi = smem_u32(smem + kOffA), a_lo = a_hi + kPartBytes;
             const uint64_t da_hi = smem_desc(a_hi), da_lo = smem_desc(a_lo);
-            const int buf = warp - (kEpi + 1);
+            const int buf = __shfl_sync(kFull, warp - (kEpi + 1), 0);
             const uint32_t d = tmem_base + (uint32_t)(buf * kDStage);
             for (int t = buf; t < n_visit; t += 2) {
                 const int s = t & (kStages - 1);
@@ -828,27 +843,31 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
                 const uint32_t b_hi = smem_u32(smem + kOffB + s * kStageStride), b_lo = b_hi + kLoOff;
                 const uint64_t db_hi = smem_desc(b_hi), db_lo = smem_desc(b_lo);
                 mbar_wait(bar_full + 8 * s, ph);                               // landed long ago, as a rule
-                FWAV_TRACE(0, t);
+                if (lane == 0) FWAV_TRACE(0, t);
                 if (!(dbg & 8)) mbar_wait(bar_tempty + 8 * buf, tph ^ 1);    // dbg 8: free-running MMA (profiling)
-                FWAV_TRACE(1, t);
+                if (lane == 0) FWAV_TRACE(1, t);
                 tc_fence_after();
-                // small cross terms first, the hi*hi term last; one K=16 instruction each
-                if (HI) {
-                    umma_f16<CG>(d, da_hi, db_hi, 0);
-                } else if (COMPACT) {
-                    umma_f16<CG>(d, da_lo, db_lo, 0);      // part 1 . part 1 = hi*lo
-                    umma_f16<CG>(d, da_hi, db_hi, 1);      // part 0 . part 0 = hi*hi + lo*hi
-                } else {
-                    umma_f16<CG>(d, da_hi, db_lo, 0);
-                    umma_f16<CG>(d, da_lo, db_hi, 1);
-                    umma_f16<CG>(d, da_hi, db_hi, 1);
+                if (elect_one()) {
+                    // small cross terms first, the hi*hi term last; one K=16 instruction each
+                    if (HI) {
+                        umma_f16<CG>(d, da_hi, db_hi, 0);
+                    } else if (COMPACT) {
+                        umma_f16<CG>(d, da_lo, db_lo, 0);      // part 1 . part 1 = hi*lo
+                        umma_f16<CG>(d, da_hi, db_hi, 1);      // part 0 . part 0 = hi*hi + lo*hi
+                    } else {
+                        umma_f16<CG>(d, da_hi, db_lo, 0);
+                        umma_f16<CG>(d, da_lo, db_hi, 1);
+                        umma_f16<CG>(d, da_hi, db_hi, 1);
+                    }
+                    umma_commit<CG>(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
+                    umma_commit<CG>(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
                 }
-                umma_commit<CG>(bar_tfull + 8 * buf);      // accumulators ready for the epilogue warps of both CTAs
-                umma_commit<CG>(bar_empty + 8 * s);        // stage free (both CTAs) once these MMAs have read it
-                FWAV_TRACE(2, t);
+                __syncwarp();
+                if (lane == 0) FWAV_TRACE(2, t);
             }
             if (dbg & 8) {   // free-running profiling mode: drain the tensor pipe before leaving
-                umma_commit<CG>(bar_a + 8 + 8 * buf);
+                if (elect_one()) umma_commit<CG>(bar_a + 8 + 8 * buf);
+                __syncwarp();
                 mbar_wait(bar_a + 8 + 8 * buf, 0);
             }
         }
@@ -1160,6 +1179,18 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 // ---------------------------------------------------------------------------
 constexpr int kHiIss = 4;
 constexpr int kHiThreads = (16 + kHiIss) * 32;
+#ifdef FWAV_DEBUG_KNOBS
+// clock64 stamps of CTA 0, stages kTraceFrom .. (FWAV_UMMA_DEBUG bit 64): issuer 0 loop top, 1 operands landed,
+// 2 accumulator free, 3 issued and committed | epilogue (quadrant 0) 4 accumulator full, 5 loaded (column half 0),
+// 6 reduced, 7 loaded (column half 1)
+#define FWAV_HI_TRACE(slot, t)                                                                               \
+    do {                                                                                                     \
+        if ((a.dbg & 64) && blockIdx.x == 0 && (t) >= kTraceFrom && (t) < kTraceFrom + kTraceStages)         \
+            a.trace[((t) - kTraceFrom) * 8 + (slot)] = clock64();                                            \
+    } while (0)
+#else
+#define FWAV_HI_TRACE(slot, t) do { } while (0)
+#endif
 constexpr uint32_t kHiOffBars = kPartBytes;                       // after the hi part of the query tile
 constexpr uint32_t kHiOffRing = 8192;                             // 1024-aligned
 constexpr uint32_t kHiStageBytes = 2 * kPartBytes;                // the two hi tiles of a 256-domain stage
@@ -1213,44 +1244,56 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
     const int t_first = s_lo + (int)((q_base / kDStage) % n_visit);
 
     if (warp >= 16) {
-        // ===== issuer + producer threads: thread i owns the stages t = i (mod 4) and their ring slots i, i + 4 =====
-        if (lane == 0) {
-            const int i = warp - 16, b = i & 1, j = i >> 1;
-            auto load_stage = [&](int t) {             // the two hi tiles of the t-th stage this CTA visits
-                int tt = t_first + t;
-                if (tt >= s_hi) tt -= n_visit;
-                const int s = t & (kStages - 1);
-                const uint32_t dst = smem_u32(smem + kHiOffRing + s * kHiStageBytes);
-                const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
+        // ===== issuer + producer warps: warp i owns the stages t = i (mod 4) and their ring slots i, i + 4 =====
+        // The whole warp runs the loop and waits; one elected lane issues.  (With a single lane inside a divergent
+        // branch the compiler cannot know that descriptors and barrier addresses are warp-uniform and wraps every
+        // tcgen05 / bulk-copy instruction in an elect-and-broadcast loop -- ~200 cycles per stage on the chain that
+        // bounds this kernel.)
+        const int i = __shfl_sync(kFull, warp - 16, 0), b = i & 1, j = i >> 1;
+        auto load_stage = [&](int t) {             // the two hi tiles of the t-th stage this CTA visits
+            int tt = t_first + t;
+            if (tt >= s_hi) tt -= n_visit;
+            const int s = t & (kStages - 1);
+            const uint32_t dst = smem_u32(smem + kHiOffRing + s * kHiStageBytes);
+            const uint4 *t0 = a.e_tiles + (2ll * tt) * (kTileBytes / 16), *t1 = t0 + kTileBytes / 16;
+            if (elect_one()) {
                 mbar_expect_tx(bar_full + 8 * s, 2 * kPartBytes);
                 bulk_g2s(dst, t0, kPartBytes, bar_full + 8 * s);
                 bulk_g2s(dst + kPartBytes, t1, kPartBytes, bar_full + 8 * s);
-            };
-            if (i == 0) {
-                mbar_expect_tx(bar_a, kPartBytes);
-                bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kPartBytes, bar_a);
             }
-            if (i < n_visit) load_stage(i);
-            mbar_wait(bar_a, 0);
-            const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
-            const uint32_t d = tmem_base + (uint32_t)(b * kDStage);
-            int k = 0;
-            for (int t = i; t < n_visit; t += kHiIss, ++k) {
-                const int tn = t + kHiIss;
-                if (tn < n_visit) {                    // next own stage: its slot was freed by this thread's own MMA of t - 4
-                    mbar_wait(bar_empty + 8 * (tn & (kStages - 1)), (uint32_t)(((tn / kStages) & 1) ^ 1));
-                    load_stage(tn);
-                }
-                const int s = t & (kStages - 1);
-                const uint64_t db_hi = smem_desc(smem_u32(smem + kHiOffRing + s * kHiStageBytes));
-                mbar_wait(bar_full + 8 * s, (uint32_t)((t / kStages) & 1));
-                // use u = t >> 1 = 2 k + j of accumulator b: its previous use has been read (nothing to wait for at u = 0)
-                if (j == 1 || k > 0) mbar_wait(bar_tfree + 8 * (2 * b + j), (uint32_t)((j == 1 ? k : k - 1) & 1));
-                tc_fence_after();
+        };
+        if (i == 0 && elect_one()) {
+            mbar_expect_tx(bar_a, kPartBytes);
+            bulk_g2s(smem_u32(smem + kOffA), a.q_tiles + (long long)group_id * (kTileBytes / 16), kPartBytes, bar_a);
+        }
+        __syncwarp();
+        if (i < n_visit) load_stage(i);
+        mbar_wait(bar_a, 0);
+        const uint64_t da_hi = smem_desc(smem_u32(smem + kOffA));
+        const uint32_t d = tmem_base + (uint32_t)(b * kDStage);
+        int k = 0;
+        for (int t = i; t < n_visit; t += kHiIss, ++k) {
+            if (lane == 0) FWAV_HI_TRACE(0, t);
+            const int tn = t + kHiIss;
+            if (tn < n_visit) {                    // next own stage: its slot was freed by this warp's own MMA of t - 4
+                mbar_wait(bar_empty + 8 * (tn & (kStages - 1)), (uint32_t)(((tn / kStages) & 1) ^ 1));
+                load_stage(tn);
+            }
+            const int s = t & (kStages - 1);
+            const uint64_t db_hi = smem_desc(smem_u32(smem + kHiOffRing + s * kHiStageBytes));
+            mbar_wait(bar_full + 8 * s, (uint32_t)((t / kStages) & 1));
+            if (lane == 0) FWAV_HI_TRACE(1, t);
+            // use u = t >> 1 = 2 k + j of accumulator b: its previous use has been read (nothing to wait for at u = 0)
+            if (j == 1 || k > 0) mbar_wait(bar_tfree + 8 * (2 * b + j), (uint32_t)((j == 1 ? k : k - 1) & 1));
+            if (lane == 0) FWAV_HI_TRACE(2, t);
+            tc_fence_after();
+            if (elect_one()) {
                 umma_f16<1, true>(d, da_hi, db_hi, 0);
                 umma_commit<1>(bar_tfull + 8 * b);
                 umma_commit<1>(bar_empty + 8 * s);
             }
+            __syncwarp();
+            if (lane == 0) FWAV_HI_TRACE(3, t);
         }
     } else {
         // ===== epilogue: one query row per thread; warp = (TMEM lane quadrant, set = accumulator, column half) =====
@@ -1271,13 +1314,15 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         int it = 0;
         for (int t = set; t < n_visit; t += 2, ++it) {
             mbar_wait_hot(bar_f, (uint32_t)(it & 1));
+            if (quad == 0 && colhalf == 0 && lane == 0) FWAV_HI_TRACE(4, t);
             tc_fence_after();
             tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
             tmem_ld32_pack16(t_lane + 64, x1);
             tmem_wait_ld2(x0, x1);
+            if (quad == 0 && lane == 0) FWAV_HI_TRACE(colhalf ? 7 : 5, t);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the thread that issues the next use
+            if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the warp that issues the next use
             const int col0 = tt * kDStage + colhalf * 128;
             tt += 2;
             if (tt >= s_hi) tt -= n_visit;
@@ -1294,6 +1339,7 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
                         ++cnt;
                     });
             }
+            if (quad == 0 && colhalf == 0 && lane == 0) FWAV_HI_TRACE(6, t);
         }
         if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
     }
@@ -1883,7 +1929,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
             // half-precision accumulators on top (single CTAs only): when (nearly) every query has room for that too
             const char *a16_env = getenv("FWAV_UMMA_ACC16");
-            acc16 = hi_only && single && !dbg && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
+            acc16 = hi_only && single && !(dbg & ~64) && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
                     (double)h_flat[2] <= 0.02 * h_flat[1];
             if (mode_env && !strcmp(mode_env, "acc16") && single && !dbg) acc16 = true;
             if (mode_env && !strcmp(mode_env, "hionly")) acc16 = false;
@@ -1948,7 +1994,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             static long long h_trace[kTraceStages * 8];
             FWAV_CUDA(ctx, cudaMemcpyAsync(h_trace, a.trace, sizeof h_trace, cudaMemcpyDeviceToHost, st));
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
-            fprintf(stderr, "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
+            fprintf(stderr, acc16 ? "# stage: loop_top operands_ok acc_free issued | acc_full loaded_h0 reduced loaded_h1 (cycles rel. to first)\n"
+                                  : "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
             const long long t0 = h_trace[0];
             for (int i = 0; i < kTraceStages; ++i) {
                 fprintf(stderr, "%4d:", kTraceFrom + i);

@@ -329,6 +329,7 @@ def run_ours(args):
         search_ms = ctx.search_timings()
     except Exception:
         search_ms = None
+    route = ctx.search_route()       # of the last timed step (later searches -- e2e, extras -- may take another one)
     for ev in all_ev:
         total_ms += ev[0].elapsed_time(ev[-1])
         for i in range(len(stage_names)):
@@ -452,7 +453,6 @@ def run_ours(args):
         peak = peaks["bf16_tflops_sustained"]
         dom_ms = search_ms["collect"] if search_ms and search_ms["collect"] > 0 else topk_ms
         fast = bool(search_ms and search_ms["collect"] > 0)
-        route = ctx.search_route()
         roof = {"kernel": ("collect_hi_kernel (hi*hi term, fp16 accumulators, one kind::f16 MMA per tile)" if route == 3 else
                            "scan_kernel<MODE_COLLECT, hi*hi> (float32 accumulators, one MMA per tile)" if route == 2 else
                            "scan_kernel<MODE_COLLECT> (full split, three MMAs per tile)" if fast else "scan_kernel<MODE_LISTS>"),
@@ -587,7 +587,9 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
                 "ms_per_pass": float(ms[0]), "ranges_per_s": n_r / (float(ms[0]) * 1e-3), "pairs": float(n_r) * n_d,
                 "pairs_per_s_per_gpu": float(n_r) * n_d / world / (float(ms[0]) * 1e-3), "warmup_passes": n_warm,
                 "search_phases_ms_rank0_last_batches": phases, "clocks": clocks,
-                "fallback_queries_rank0": ctx.search_fallbacks()}
+                "fallback_queries_rank0": ctx.search_fallbacks(),
+                "search_route_rank0_last_batch": {0: "lists", 1: "full split", 2: "hi*hi, float32 accumulators",
+                                                  3: "hi*hi, fp16 accumulators"}.get(ctx.search_route(), "?")}
         return info, res, (t_sig, t_rng, tile, k, N)
 
     def verify_sample(res, t_rng, tile, k, N, n_check=24):

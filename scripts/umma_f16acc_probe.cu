@@ -40,14 +40,27 @@ __device__ __forceinline__ uint64_t desc_none(uint32_t saddr, uint32_t lbo, uint
                "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
 
 // mode bit 0: D format (0 = f16 accumulators, 1 = f32); bit 1: use tcgen05.ld ... pack::16b for the dump
+// A2 / B2 (may be null): a second operand pair issued FIRST (D = A2*B2, then D += A*B) -- the "bias" command
 __global__ void __launch_bounds__(160) probe_kernel(const __half *A, const __half *B, uint32_t *dump, long long *cycles,
-                                                    int mode, int n_rep) {
+                                                    int mode, int n_rep, const __half *A2 = nullptr, const __half *B2 = nullptr) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __half *sa = reinterpret_cast<__half *>(smem);             // 128 x 16
     __half *sb = reinterpret_cast<__half *>(smem + 4096);      // 256 x 16
     const uint32_t bar = smem_u32(smem + 4096 + 8192);
     uint32_t *slot = reinterpret_cast<uint32_t *>(smem + 4096 + 8192 + 16);
+    __half *sa2 = reinterpret_cast<__half *>(smem + 16384);    // only with A2 (the launch then asks for 28 KB + 64)
+    __half *sb2 = reinterpret_cast<__half *>(smem + 16384 + 4096);
+    if (A2) {
+        for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+            const int r = i / 16, k = i % 16;
+            sa2[(k / 8) * (128 * 8) + (r / 8) * 64 + (r % 8) * 8 + (k % 8)] = A2[i];
+        }
+        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+            const int r = i / 16, k = i % 16;
+            sb2[(k / 8) * (256 * 8) + (r / 8) * 64 + (r % 8) * 8 + (k % 8)] = B2[i];
+        }
+    }
     // stage operands in the canonical no-swizzle K-major layout
     for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
         const int r = i / 16, k = i % 16;
@@ -75,10 +88,17 @@ __global__ void __launch_bounds__(160) probe_kernel(const __half *A, const __hal
         const uint32_t idesc = (c_fmt << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t da = desc_none(smem_u32(sa), 128 * 16, 128), db = desc_none(smem_u32(sb), 256 * 16, 128);
         const long long t0 = clock64();
-        for (int i = 0; i < n_rep; ++i)
+        for (int i = 0; i < n_rep; ++i) {
+            if (A2) {
+                const uint64_t da2 = desc_none(smem_u32(sa2), 128 * 16, 128), db2 = desc_none(smem_u32(sb2), 256 * 16, 128);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da2), "l"(db2), "r"(idesc), "r"(0)
+                             : "memory");
+            }
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(0)
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(A2 ? 1 : 0)
                          : "memory");
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
         mbar_wait(bar, 0);
         cycles[0] = clock64() - t0;
@@ -185,8 +205,83 @@ static int accuracy(int n_launch) {
     return 0;
 }
 
+// "bias" command (round 2): the threshold inside the accumulator.  D = A2*B2 (row r: -t_r, t_r a half-precision
+// number) followed by D += A*B leaves score - t in the accumulator, so "reaches the threshold" is a sign bit.  How far
+// is the delivered value from the exact (score - t), and how close to zero must the exact value be for the SIGN to be
+// wrong?  Thresholds are taken from the row's own scores (rounded down to fp16), so near-ties are plentiful.
+static int bias(int n_launch) {
+    static __half hA[128 * 16], hB[256 * 16], hA2[128 * 16], hB2[256 * 16];
+    static uint32_t hD[128 * 256];
+    __half *dA, *dB, *dA2, *dB2;
+    uint32_t *dD;
+    long long *dC;
+    cudaMalloc(&dA, sizeof hA); cudaMalloc(&dB, sizeof hB); cudaMalloc(&dA2, sizeof hA); cudaMalloc(&dB2, sizeof hB);
+    cudaMalloc(&dD, 128 * 256 * 4); cudaMalloc(&dC, 8);
+    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 28672 + 64);
+    unsigned long long st = 88172645463325252ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    auto gauss = [&]() { double u = rnd() + 1e-12, v = rnd(); return sqrt(-2 * log(u)) * cos(6.283185307179586 * v); };
+    for (int fmt = 0; fmt < 2; ++fmt) {
+        double max_err = 0, worst_wrong_sign = 0, max_err_small = 0;
+        long long n = 0, n_wrong = 0, n_small = 0;
+        for (int l = 0; l < n_launch; ++l) {
+            auto fill = [&](__half *dst, int rows) {
+                for (int r = 0; r < rows; ++r) {
+                    double x[16], n0 = 0, n1 = 0;
+                    for (int k = 0; k < 16; ++k) { x[k] = gauss(); (k < 8 ? n0 : n1) += x[k] * x[k]; }
+                    for (int k = 0; k < 16; ++k) {
+                        double v = x[k] / sqrt(k < 8 ? n0 : n1);
+                        if (l % 4 == 3) v = 0.97 * (k % 8 == 0 ? 1.0 : 0.05) + 0.03 * v;
+                        dst[r * 16 + k] = __float2half((float)v);
+                    }
+                }
+            };
+            fill(hA, 128); fill(hB, 256);
+            memset(hA2, 0, sizeof hA2); memset(hB2, 0, sizeof hB2);
+            static double thr[128];
+            for (int r = 0; r < 128; ++r) {
+                // the threshold of row r: the exact score of column (r * 7) % 256, moved by 0 .. 3 fp16 steps, rounded down
+                const int c = (r * 7) % 256;
+                double ex = 0;
+                for (int k = 0; k < 16; ++k) ex += (double)__half2float(hA[r * 16 + k]) * (double)__half2float(hB[c * 16 + k]);
+                __half t = __float2half_rd((float)fabs(ex));
+                __half_raw tr = t; tr.x = (unsigned short)(tr.x + (r % 4)); t = __half(tr);
+                thr[r] = __half2float(t);
+                hA2[r * 16] = __float2half(-(float)thr[r]);
+            }
+            for (int c = 0; c < 256; ++c) hB2[c * 16] = __float2half(1.0f);
+            cudaMemcpy(dA, hA, sizeof hA, cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, sizeof hB, cudaMemcpyHostToDevice);
+            cudaMemcpy(dA2, hA2, sizeof hA, cudaMemcpyHostToDevice); cudaMemcpy(dB2, hB2, sizeof hB, cudaMemcpyHostToDevice);
+            probe_kernel<<<1, 160, 28672 + 64>>>(dA, dB, dD, dC, fmt, 1, dA2, dB2);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("launch failed\n"); return 1; }
+            cudaMemcpy(hD, dD, sizeof hD, cudaMemcpyDeviceToHost);
+            for (int r = 0; r < 128; ++r)
+                for (int c = 0; c < 256; ++c) {
+                    double ex = -thr[r];
+                    for (int k = 0; k < 16; ++k) ex += (double)__half2float(hA[r * 16 + k]) * (double)__half2float(hB[c * 16 + k]);
+                    double got;
+                    unsigned sign;
+                    if (fmt) { float f; memcpy(&f, &hD[r * 256 + c], 4); got = f; sign = hD[r * 256 + c] >> 31; }
+                    else { __half_raw h; h.x = hD[r * 256 + c] & 0xffff; got = __half2float(__half(h)); sign = (h.x >> 15) & 1; }
+                    const double err = fabs(got - ex);
+                    if (err > max_err) max_err = err;
+                    if (fabs(ex) < 4e-3) { ++n_small; if (err > max_err_small) max_err_small = err; }
+                    const bool wrong = (sign != 0) != (ex < 0);
+                    if (wrong) { ++n_wrong; if (fabs(ex) > worst_wrong_sign) worst_wrong_sign = fabs(ex); }
+                    ++n;
+                }
+        }
+        printf("{\"probe\": \"threshold inside the accumulator\", \"accumulators\": \"%s\", \"scores\": %lld, \"max_abs_err\": %.3e, "
+               "\"scores_within_4e-3_of_threshold\": %lld, \"max_abs_err_there\": %.3e, \"wrong_signs\": %lld, "
+               "\"largest_exact_distance_with_a_wrong_sign\": %.3e}\n",
+               fmt ? "f32" : "f16", n, max_err, n_small, max_err_small, n_wrong, worst_wrong_sign);
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "acc")) return accuracy(argc > 2 ? atoi(argv[2]) : 100);
+    if (argc > 1 && !strcmp(argv[1], "bias")) return bias(argc > 2 ? atoi(argv[2]) : 100);
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const int n_rep = argc > 2 ? atoi(argv[2]) : 1;
     __half hA[128 * 16], hB[256 * 16];
