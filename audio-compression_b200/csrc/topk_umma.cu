@@ -1323,6 +1323,11 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the warp that issues the next use
+            // The hand-back is on the chain that bounds the kernel and nothing in this warp depends on it, so the
+            // instruction scheduler sinks it below the first levels of the max tree (~30 instructions).  A wait that
+            // always passes (the query tile's barrier completed its only phase at the start) is a loop the scheduler
+            // does not move code across: the hand-back stays up here.
+            mbar_wait_hot(bar_a, 0);
             const int col0 = tt * kDStage + colhalf * 128;
             tt += 2;
             if (tt >= s_hi) tt -= n_visit;
