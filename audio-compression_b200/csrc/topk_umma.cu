@@ -271,6 +271,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_wait_ld1(uint32_t (&a)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a)::"memory");
 }
+// the compiler forgets what it knows about the 32 values (nothing is emitted): a rare path that starts with this
+// recomputes what it needs instead of keeping the common path's intermediate results alive in registers
+// (`after`: a value the common path ends with, so that this cannot move above it)
+__device__ __forceinline__ void launder32(uint32_t (&a)[32], unsigned after) { asm volatile("" : FWAV_RW32(a) : "r"(after)); }
 __device__ __forceinline__ void tmem_wait_ld2(uint32_t (&a)[32], uint32_t (&b)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : FWAV_RW32(a), FWAV_RW32(b)::"memory");
 }
@@ -1180,21 +1184,31 @@ __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(n_threads(MODE), 1)
 constexpr int kHiIss = 4;
 constexpr int kHiThreads = (16 + kHiIss) * 32;
 #ifdef FWAV_DEBUG_KNOBS
-// clock64 stamps of CTA 0, stages kTraceFrom .. (FWAV_UMMA_DEBUG bit 64): issuer 0 loop top, 1 operands landed,
+// clock64 stamps of one CTA (FWAV_UMMA_DEBUG bit 64; bits 16-23: first stage / 64, bits 24-30: CTA / 32): issuer 0 loop top, 1 operands landed,
 // 2 accumulator free, 3 issued and committed | epilogue (quadrant 0) 4 accumulator full, 5 loaded (column half 0),
 // 6 reduced, 7 loaded (column half 1)
 #define FWAV_HI_TRACE(slot, t)                                                                               \
     do {                                                                                                     \
-        if ((a.dbg & 64) && blockIdx.x == 0 && (t) >= kTraceFrom && (t) < kTraceFrom + kTraceStages)         \
-            a.trace[((t) - kTraceFrom) * 8 + (slot)] = clock64();                                            \
+        if ((a.dbg & 64) && (int)blockIdx.x == ((a.dbg >> 24) & 0x7f) * 32 && (t) >= ((a.dbg >> 16) & 0xff) * 64 &&   \
+            (t) < ((a.dbg >> 16) & 0xff) * 64 + kTraceStages)                                                \
+            a.trace[((t) - ((a.dbg >> 16) & 0xff) * 64) * 8 + (slot)] = clock64();                           \
     } while (0)
 #else
 #define FWAV_HI_TRACE(slot, t) do { } while (0)
 #endif
+// stamps inside the epilogue warps cost them registers (the loop runs at the 96-register limit) and slow the kernel
+// down by a third even when switched off at run time: compiled only with -DFWAV_TRACE_EPILOGUE (bit 128 switches them on)
+#if defined(FWAV_DEBUG_KNOBS) && defined(FWAV_TRACE_EPILOGUE)
+#define FWAV_HI_TRACE_EPI(cond, slot, t) do { if ((a.dbg & 128) && (cond)) FWAV_HI_TRACE(slot, t); } while (0)
+#else
+#define FWAV_HI_TRACE_EPI(cond, slot, t) do { } while (0)
+#endif
 constexpr uint32_t kHiOffBars = kPartBytes;                       // after the hi part of the query tile
 constexpr uint32_t kHiOffRing = 8192;                             // 1024-aligned
 constexpr uint32_t kHiStageBytes = 2 * kPartBytes;                // the two hi tiles of a 256-domain stage
-constexpr uint32_t kHiSmem = kHiOffRing + kStages * kHiStageBytes;
+constexpr uint32_t kHiOffScratch = kHiOffRing + kStages * kHiStageBytes;   // per epilogue warp: a 32 x 33-word transpose buffer
+constexpr uint32_t kHiScratchWords = 32 * 33;
+constexpr uint32_t kHiSmem = kHiOffScratch + 16 * kHiScratchWords * 4;
 
 __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -1277,7 +1291,9 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             const int tn = t + kHiIss;
             if (tn < n_visit) {                    // next own stage: its slot was freed by this warp's own MMA of t - 4
                 mbar_wait(bar_empty + 8 * (tn & (kStages - 1)), (uint32_t)(((tn / kStages) & 1) ^ 1));
+                if (lane == 0 && !(a.dbg & 128)) FWAV_HI_TRACE(4, t);
                 load_stage(tn);
+                if (lane == 0 && !(a.dbg & 128)) FWAV_HI_TRACE(5, t);
             }
             const int s = t & (kStages - 1);
             const uint64_t db_hi = smem_desc(smem_u32(smem + kHiOffRing + s * kHiStageBytes));
@@ -1299,8 +1315,11 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         // ===== epilogue: one query row per thread; warp = (TMEM lane quadrant, set = accumulator, column half) =====
         const int quad = warp & 3, half = warp >> 2, set = half & 1, colhalf = half >> 1;
         const long long q = q_base + quad * 32 + lane;
+#ifdef FWAV_DEBUG_KNOBS
+        const float tau = (q < n_q && !(a.dbg & 256)) ? a.theta[q] : INFINITY;      // dbg 256: no hits in this kernel (profiling)
+#else
         const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
-        int32_t *cbuf = a.cbuf + (((q < n_q ? q : 0) * a.n_split + split) * 4 + half) * (long long)a.cap;
+#endif
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kDStage + colhalf * 128);
         const uint32_t bar_f = bar_tfull + 8 * set;
         int cnt = 0;
@@ -1312,14 +1331,47 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         const float tpos = tau > 0.0f ? tau : 0.0f;
         const unsigned t1x2 = (unsigned)(((int)__half_as_ushort(__float2half_rd(tpos)) - 1) & 0xffff) * 0x10001u;
         int it = 0;
+        // Hits.  A row's hits sit in registers only its own lane can index, and only with constant indices: walking
+        // them lane by lane costs a tree of divergent branches per hit (and 30 KB of unrolled code), which stalls the
+        // whole set where hits are dense (a query's own neighbourhood).  Instead the warp turns a chunk with hits by
+        // 90 degrees through shared memory: every lane stores its 32 registers (conflict-free, 33-word rows), then for
+        // each row with a hit lane j reads that row's register j -- one load -- and all 64 columns of the row are
+        // compared at once; ballots give every hit its place in the row's buffer, so the indices of a row leave as
+        // neighbouring stores.  No divergence, no data-dependent register index.
+        uint32_t *scr = reinterpret_cast<uint32_t *>(smem + kHiOffScratch) + warp * kHiScratchWords;
+        int32_t *cbuf_warp = a.cbuf + (((q_base + quad * 32) * a.n_split + split) * 4 + half) * (long long)a.cap;   // row 0 of the warp
+        const long long cbuf_row = (long long)a.n_split * 4 * a.cap;
+        const unsigned lane_lt = (1u << lane) - 1u;
+        auto extract = [&](const uint32_t (&x)[32], unsigned m, int colbase) {
+            unsigned rows_hit = __ballot_sync(kFull, p_beats(m, t1x2));
+            if (rows_hit == 0) return;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scr[j * 33 + lane] = x[j];
+            __syncwarp();
+            do {
+                const int r = __ffs(rows_hit) - 1;
+                rows_hit &= rows_hit - 1;
+                const unsigned v = scr[lane * 33 + r];                  // register `lane` of row r: its columns 2 lane, 2 lane + 1
+                const unsigned tr = __shfl_sync(kFull, t1x2, r);
+                const unsigned gt = __vcmpgts2(v, tr);                  // 0xffff per half that exceeds the row's threshold
+                const unsigned b_lo = __ballot_sync(kFull, (gt & 0xffffu) != 0), b_hi = __ballot_sync(kFull, (gt >> 16) != 0);
+                const int cnt_r = __shfl_sync(kFull, cnt, r);
+                int32_t *cb = cbuf_warp + r * cbuf_row;
+                const int p_lo = cnt_r + __popc(b_lo & lane_lt), p_hi = cnt_r + __popc(b_lo) + __popc(b_hi & lane_lt);
+                if ((gt & 0xffffu) && p_lo < a.cap) cb[p_lo] = colbase + 2 * lane;
+                if ((gt >> 16) && p_hi < a.cap) cb[p_hi] = colbase + 2 * lane + 1;
+                if (lane == r) cnt = cnt_r + __popc(b_lo) + __popc(b_hi);
+            } while (rows_hit);
+            __syncwarp();
+        };
         for (int t = set; t < n_visit; t += 2, ++it) {
             mbar_wait_hot(bar_f, (uint32_t)(it & 1));
-            if (quad == 0 && colhalf == 0 && lane == 0) FWAV_HI_TRACE(4, t);
+            FWAV_HI_TRACE_EPI(quad == 0 && colhalf == 0 && lane == 0, 4, t);
             tc_fence_after();
             tmem_ld32_pack16(t_lane, x0);            // this warp's 128 columns of the stage, in one round
             tmem_ld32_pack16(t_lane + 64, x1);
             tmem_wait_ld2(x0, x1);
-            if (quad == 0 && lane == 0) FWAV_HI_TRACE(colhalf ? 7 : 5, t);
+            FWAV_HI_TRACE_EPI(quad == 0 && lane == 0, colhalf ? 7 : 5, t);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the warp that issues the next use
@@ -1332,19 +1384,11 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             tt += 2;
             if (tt >= s_hi) tt -= n_visit;
             const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
-            if (p_beats(pmax3(m0, m1, m1), t1x2)) {
-                if (p_beats(m0, t1x2))
-                    for_each_gt_p(x0, t1x2, [&](int jj) {
-                        if (cnt < a.cap) cbuf[cnt] = col0 + jj;
-                        ++cnt;
-                    });
-                if (p_beats(m1, t1x2))
-                    for_each_gt_p(x1, t1x2, [&](int jj) {
-                        if (cnt < a.cap) cbuf[cnt] = col0 + 64 + jj;
-                        ++cnt;
-                    });
+            if (__any_sync(kFull, p_beats(pmax3(m0, m1, m1), t1x2))) {
+                extract(x0, m0, col0);
+                extract(x1, m1, col0 + 64);
             }
-            if (quad == 0 && colhalf == 0 && lane == 0) FWAV_HI_TRACE(6, t);
+            FWAV_HI_TRACE_EPI(quad == 0 && colhalf == 0 && lane == 0, 6, t);
         }
         if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
     }
@@ -1934,7 +1978,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
             // half-precision accumulators on top (single CTAs only): when (nearly) every query has room for that too
             const char *a16_env = getenv("FWAV_UMMA_ACC16");
-            acc16 = hi_only && single && !(dbg & ~64) && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
+            acc16 = hi_only && single && !(dbg & 0xffff & ~(64 | 128 | 256)) && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
                     (double)h_flat[2] <= 0.02 * h_flat[1];
             if (mode_env && !strcmp(mode_env, "acc16") && single && !dbg) acc16 = true;
             if (mode_env && !strcmp(mode_env, "hionly")) acc16 = false;
@@ -2003,7 +2047,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                                   : "# stage: full_ok tempty_ok issued | ld_a_done released early_try look_b_done late_wait_done (cycles rel. to first)\n");
             const long long t0 = h_trace[0];
             for (int i = 0; i < kTraceStages; ++i) {
-                fprintf(stderr, "%4d:", kTraceFrom + i);
+                fprintf(stderr, "%4d:", (acc16 ? ((dbg >> 16) & 0xff) * 64 : kTraceFrom) + i);
                 for (int k = 0; k < 8; ++k) fprintf(stderr, " %8lld", h_trace[i * 8 + k] ? h_trace[i * 8 + k] - t0 : -1ll);
                 fprintf(stderr, "\n");
             }

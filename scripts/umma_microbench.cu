@@ -109,6 +109,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 64 columns, two 16-bit halves per register (half-precision accumulators)
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ unsigned chunk_max_p(const uint32_t (&v)[32]) {
+    unsigned m[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) m[i] = __vimax3_s16x2(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    m[10] = __vimax3_s16x2(v[30], v[31], v[31]);
+    const unsigned a = __vimax3_s16x2(m[0], m[1], m[2]), b = __vimax3_s16x2(m[3], m[4], m[5]), c = __vimax3_s16x2(m[6], m[7], m[8]);
+    return __vimax3_s16x2(__vimax3_s16x2(a, b, c), m[9], m[10]);
+}
 __device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : RW32(v)::"memory");
 }
@@ -212,7 +233,24 @@ __global__ void __launch_bounds__((NLDW + 1) * 32, 1) bench_kernel(Params p, lon
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * NCH * 32);
         uint32_t sink = 0;
         t0 = clock64();
-        if (p.ld_mode <= 1) {
+        if (p.ld_mode >= 3) {
+            // half-precision accumulators: pack::16b loads, 64 columns each (mode 4: + the packed 3-input max tree)
+            constexpr int NP = NCH / 2;
+            for (int it = 0; it < p.ld_iters; ++it) {
+                const uint32_t ta = t_lane + (uint32_t)((it & 1) * 256);
+                uint32_t v[NP][32];
+#pragma unroll
+                for (int c = 0; c < NP; ++c) tmem_ld32_pack16(ta + 64 * c, v[c]);
+#pragma unroll
+                for (int c = 0; c < NP; ++c) tmem_wait_ld(v[c]);
+                if (p.ld_mode == 4) {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) sink += chunk_max_p(v[c]) != 0x7fff7fffu ? 1u : 0u;
+                } else {
+                    sink ^= v[0][0] ^ v[NP - 1][31];
+                }
+            }
+        } else if (p.ld_mode <= 1) {
             for (int it = 0; it < p.ld_iters; ++it) {
                 const int buf = it & 1;
                 if (p.sync_mode) {
@@ -368,6 +406,13 @@ int main(int argc, char **argv) {
     vs.push_back(mk("ld_8w_max", 1, 128, 128, "sw32", "sw32", 0, 0, 8, 4096, 1, 0));
     vs.push_back(mk("ld_4w_max", 1, 128, 128, "sw32", "sw32", 0, 0, 4, 4096, 1, 0));
     vs.push_back(mk("ld_8w_max_pipelined", 1, 128, 128, "sw32", "sw32", 0, 0, 8, 4096, 2, 0));
+    vs.push_back(mk("ld_8w_pack16", 1, 128, 128, "sw32", "sw32", 0, 0, 8, 4096, 3, 0));
+    vs.push_back(mk("ld_16w_pack16", 1, 128, 128, "sw32", "sw32", 0, 0, 16, 4096, 3, 0));
+    vs.push_back(mk("ld_4w_pack16", 1, 128, 128, "sw32", "sw32", 0, 0, 4, 4096, 3, 0));
+    vs.push_back(mk("ld_1w_pack16", 1, 128, 128, "sw32", "sw32", 0, 0, 1, 4096, 3, 0));
+    vs.push_back(mk("ld_1w", 1, 128, 128, "sw32", "sw32", 0, 0, 1, 4096, 0, 0));
+    vs.push_back(mk("ld_8w_pack16_max", 1, 128, 128, "sw32", "sw32", 0, 0, 8, 4096, 4, 0));
+    vs.push_back(mk("ld_16w_pack16_max", 1, 128, 128, "sw32", "sw32", 0, 0, 16, 4096, 4, 0));
     vs.push_back(mk("ld_16w", 1, 128, 128, "sw32", "sw32", 0, 0, 16, 4096, 0, 0));
     vs.push_back(mk("ld_16w_max", 1, 128, 128, "sw32", "sw32", 0, 0, 16, 4096, 1, 0));
     vs.push_back(mk("ld_16w_max_pipelined", 1, 128, 128, "sw32", "sw32", 0, 0, 16, 4096, 2, 0));
