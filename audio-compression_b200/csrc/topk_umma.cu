@@ -1364,6 +1364,7 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             } while (rows_hit);
             __syncwarp();
         };
+        uint32_t bar_back = bar_tfree + 8 * (2 * set + 1);      // the issuers of an accumulator take turns: 2 set + ((it + 1) & 1)
         for (int t = set; t < n_visit; t += 2, ++it) {
             mbar_wait_hot(bar_f, (uint32_t)(it & 1));
             FWAV_HI_TRACE_EPI(quad == 0 && colhalf == 0 && lane == 0, 4, t);
@@ -1374,7 +1375,8 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             FWAV_HI_TRACE_EPI(quad == 0 && lane == 0, colhalf ? 7 : 5, t);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_local(bar_tfree + 8 * (2 * set + ((it + 1) & 1)));     // to the warp that issues the next use
+            if (lane == 0) mbar_arrive_local(bar_back);     // to the warp that issues the next use
+            bar_back ^= 8u;
             // The hand-back is on the chain that bounds the kernel and nothing in this warp depends on it, so the
             // instruction scheduler sinks it below the first levels of the max tree (~30 instructions).  A wait that
             // always passes (the query tile's barrier completed its only phase at the start) is a loop the scheduler
