@@ -1962,7 +1962,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         // streaming modes: CTAs on their own by default (FWAV_UMMA_CG=2: CTA pairs)
         const long long groups = single ? (nq + kQTile - 1) / kQTile : pairs;
         if ((rc = compact ? launch_scan<MODE_THETA, false, 1, true>(ctx, a, groups, 1, st)
-                  : single ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st)
+                  // (on its own CTA the threshold pass takes the hi*hi term alone: a threshold is an estimate anyway, and
+                  // the proof of a query never relies on how it was obtained; FWAV_UMMA_THETA_FULL=1: the full split)
+                  : single ? (getenv("FWAV_UMMA_THETA_FULL") ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st)
+                                                             : launch_scan<MODE_THETA, true, 1>(ctx, a, groups, 1, st))
                            : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
             return rc;
         // may pass 2 filter with the hi*hi term too?  Only if (nearly) every query has room for its error bound

@@ -3,6 +3,7 @@
 set +e
 O=gpurun_out; mkdir -p $O
 L=$PWD/audio-compression_b200/fwav_b200/libfwav_b200_dbg.so
+for d in 0 256; do FWAV_LIB=$L FWAV_UMMA_DEBUG=$d timeout 200 python scripts/time_topk.py 1.0 umma 2 2>/dev/null | cut -c1-160; done
 # (first stage / 64, CTA / 32): own neighbourhood, far away, a late CTA
 for w in "0 0" "1 0" "60 0" "4 60" "60 60" "100 120"; do
   set -- $w
