@@ -463,14 +463,19 @@ def run_ours(args):
                                "profiles/r02_umma_microbench.jsonl)",
                 "search_stage_ms": topk_ms, "search_phases_ms": search_ms,
                 "achieved_whole_search_stage": flops / (topk_ms * 1e-3) / 1e12}
-        # what actually bounds a K = 16 contraction: every score leaves TMEM once (512 B/clk/SM, one 32-bit column per
-        # score whatever the accumulator format) and goes through a 3-input max tree on the ALU pipe (17 half-rate
-        # instructions per 32 registers and scheduler; a register holds two scores with fp16 accumulators)
+        # what actually bounds a K = 16 contraction, from microbenchmarks on B200 (cycles per 128 x 256 stage and SM;
+        # profiles/r02_tmem_ld_microbench.jsonl, r02_pipe_microbench.jsonl): every score leaves TMEM once (257 cycles with
+        # float32 accumulators, 131 with fp16 ones read two per register) and goes through a 3-input max tree (one
+        # dispatch cycle per input register); loads and tree together, free-running: 214 cycles (fp16) / 409 (float32).
+        # With two accumulators in TMEM the hand-over chain MMA -> commit -> load -> hand-back -> MMA adds its own floor:
+        # 688 cycles per use of an accumulator traced where there are no hits.
         clk = peaks["sm_max_mhz"] * 1e6
-        scores = pairs / world
-        per_reg = 2.0 if route == 3 else 1.0
-        roof["epilogue_floor_ms"] = {"tmem_drain": 1e3 * scores * 4.0 / (512.0 * 148 * clk),
-                                     "alu_max_tree": 1e3 * scores / per_reg * (17.0 / 32.0) * 2.0 / (128.0 * 148 * clk)}
+        stages = pairs / world / (128.0 * 256.0) / 148.0
+        cyc = {"tmem_drain": 131.0, "alu_max_tree": 2 * 34 * 2.0, "loads_and_tree_measured": 214.0} if route == 3 else \
+              {"tmem_drain": 257.0, "alu_max_tree": 2 * 68 * 2.0, "loads_and_tree_measured": 409.0}
+        roof["epilogue_floor_ms"] = {k: 1e3 * stages * v / clk for k, v in cyc.items()}
+        if route == 3:
+            roof["handover_chain_floor_ms"] = 1e3 * stages * 344.0 / clk
         roof["frac_of_epilogue_floor"] = max(roof["epilogue_floor_ms"].values()) / dom_ms
         topk_ms_roof = dom_ms
     else:
