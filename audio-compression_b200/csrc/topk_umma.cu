@@ -1416,13 +1416,11 @@ constexpr int kFinWarps = 4;
 constexpr int kFinKeys = 768;          // keys per query the shared-memory path of the first finalize holds (the second chance: all)
 constexpr int kFinRegs = 10;           // candidates per lane the register path of finalize_kernel holds (320 per query)
 
+// two hardware reductions (REDUX.MAX.U32): the largest high word, then the largest low word among its holders
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(kFull, x, o);
-        x = y > x ? y : x;
-    }
-    return x;
+    const unsigned hi = __reduce_max_sync(kFull, (unsigned)(x >> 32));
+    const unsigned lo = __reduce_max_sync(kFull, (unsigned)(x >> 32) == hi ? (unsigned)x : 0u);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 __global__ void __launch_bounds__(kFinWarps * 32)
@@ -1690,6 +1688,7 @@ namespace {
 constexpr int kCollectCap = 256;              // candidate indices kept per (query, column group of 64)
 constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta is the 24th best sampled score there)
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
+constexpr double kFailWeight = 2.5;           // route choice: passes' worth of second chance per fraction of queries without room
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
 constexpr bool kDefaultAcc16 = true;          // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16=0: off)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
@@ -1979,12 +1978,23 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             FWAV_CUDA(ctx, cudaStreamSynchronize(st));
             // (a query without that room is not lost: it fails verification and takes the second chance below,
             // which is cheap next to the +35 % of a full-split pass)
-            hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.02 * h_flat[1];
-            if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
-            // half-precision accumulators on top (single CTAs only): when (nearly) every query has room for that too
             const char *a16_env = getenv("FWAV_UMMA_ACC16");
-            acc16 = hi_only && single && !(dbg & 0xffff & ~(64 | 128 | 256)) && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16) &&
-                    (double)h_flat[2] <= 0.02 * h_flat[1];
+            const bool a16_ok = single && !(dbg & 0xffff & ~(64 | 128 | 256)) && (a16_env ? atoi(a16_env) != 0 : kDefaultAcc16);
+            if (compact || h_flat[1] == 0) {
+                // (compact tiles carry hi and lo in one part: no hi*hi-only form of them)
+                hi_only = h_flat[1] > 0 && (double)h_flat[0] <= 0.02 * h_flat[1];
+                acc16 = hi_only && a16_ok && (double)h_flat[2] <= 0.02 * h_flat[1];
+            } else {
+                // The cheapest of three, in units of the fp16-accumulator pass over the whole batch (measured on config 2:
+                // float32 accumulators 1.35, full split 1.85).  A query that lacks the room MAY fail its proof (on config 2
+                // one in four does) and then costs a second chance: full split, own launch, partial waves -- kFailWeight
+                // passes' worth per failing fraction, a deliberately pessimistic figure.
+                const double f16 = (double)h_flat[2] / h_flat[1], f32 = (double)h_flat[0] / h_flat[1];
+                const double c16 = a16_ok ? 1.0 + kFailWeight * f16 : 1e30, c32 = 1.35 + kFailWeight * f32, cfull = 1.85;
+                acc16 = c16 <= c32 && c16 <= cfull;
+                hi_only = acc16 || c32 <= cfull;
+            }
+            if (mode_env && (!strcmp(mode_env, "hionly") || !strcmp(mode_env, "acc16"))) hi_only = true;
             if (mode_env && !strcmp(mode_env, "acc16") && single && !dbg) acc16 = true;
             if (mode_env && !strcmp(mode_env, "hionly")) acc16 = false;
             if (getenv("FWAV_UMMA_VERBOSE"))
