@@ -1210,6 +1210,15 @@ constexpr uint32_t kHiOffScratch = kHiOffRing + kStages * kHiStageBytes;   // pe
 constexpr uint32_t kHiScratchWords = 32 * 33;
 constexpr uint32_t kHiSmem = kHiOffScratch + 16 * kHiScratchWords * 4;
 
+// THETA = true: the same skeleton as pass 1 of the fast path (thresholds from the sampled table, a.theta / a.theta_hi
+// out).  No indices, no hits: a lane keeps, per parity of the column (the two halves of a packed register), the three
+// largest CHUNK MAXIMA of its (accumulator, column half) group -- a packed insertion of six 2-input min / max
+// instructions per 64-column chunk, unconditional -- and at the end the 4 x 6 values of a row are merged.  The r-th
+// largest of such maxima can only be at or below the r-th largest sampled score (more candidates, never fewer); the
+// sample tiles are dealt so that neighbouring samples of one similarity peak land in different (group, parity)
+// streams (pack_f16_tiles_kernel).  Scores are fp16 here: a threshold is an estimate, and no proof depends on how it
+// was obtained.
+template <bool THETA>
 __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1232,8 +1241,10 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         if (!__syncthreads_or(any)) {
             for (int i = threadIdx.x; i < kQTile; i += kHiThreads) {
                 const long long q = q_base + i;
-                if (q < n_q)
-                    for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+                if (q < n_q) {
+                    if (THETA) { a.theta[q] = INFINITY; a.theta_hi[q] = INFINITY; }
+                    else for (int g = 0; g < 4; ++g) a.ccount[(q * a.n_split + split) * 4 + g] = 0;
+                }
             }
             return;
         }
@@ -1316,10 +1327,17 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         const int quad = warp & 3, half = warp >> 2, set = half & 1, colhalf = half >> 1;
         const long long q = q_base + quad * 32 + lane;
 #ifdef FWAV_DEBUG_KNOBS
-        const float tau = (q < n_q && !(a.dbg & 256)) ? a.theta[q] : INFINITY;      // dbg 256: no hits in this kernel (profiling)
+        const float tau = (!THETA && q < n_q && !(a.dbg & 256)) ? a.theta[q] : INFINITY;      // dbg 256: no hits in this kernel (profiling)
 #else
-        const float tau = q < n_q ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
+        const float tau = (!THETA && q < n_q) ? a.theta[q] : INFINITY;      // +inf for pruned rows (written by pass 1)
 #endif
+        // THETA: the three largest chunk maxima per parity, descending (signed 16-bit order, see pmax3)
+        unsigned top0 = 0x80008000u, top1 = 0x80008000u, top2 = 0x80008000u;
+        auto keep = [&](unsigned v) {
+            unsigned h = __vmaxs2(top0, v); v = __vmins2(top0, v); top0 = h;
+            h = __vmaxs2(top1, v); v = __vmins2(top1, v); top1 = h;
+            top2 = __vmaxs2(top2, v);
+        };
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kDStage + colhalf * 128);
         const uint32_t bar_f = bar_tfull + 8 * set;
         int cnt = 0;
@@ -1386,13 +1404,53 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
             tt += 2;
             if (tt >= s_hi) tt -= n_visit;
             const unsigned m0 = chunk_max_p(x0), m1 = chunk_max_p(x1);
-            if (__any_sync(kFull, p_beats(pmax3(m0, m1, m1), t1x2))) {
+            if (THETA) {
+                keep(m0);
+                keep(m1);
+            } else if (__any_sync(kFull, p_beats(pmax3(m0, m1, m1), t1x2))) {
                 extract(x0, m0, col0);
                 extract(x1, m1, col0 + 64);
             }
             FWAV_HI_TRACE_EPI(quad == 0 && colhalf == 0 && lane == 0, 6, t);
         }
-        if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
+        if (!THETA) {
+            if (q < n_q) a.ccount[(q * a.n_split + split) * 4 + half] = cnt;
+        } else {
+            // theta of a row = the theta_rank-th largest of its 4 groups x 2 parities x 3 kept maxima (the transpose
+            // buffers of the collect pass, unused here, carry them to the group-0 lanes)
+            float *th = reinterpret_cast<float *>(smem + kHiOffScratch);      // [row][4][6]
+            const int row = quad * 32 + lane;
+            const bool live = q < n_q && (!active || active[q]);
+            const unsigned tops[3] = {top0, top1, top2};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                // a slot that never saw a score (0x8000 = -0) counts as -inf
+                const unsigned short lo16 = (unsigned short)(tops[i] & 0xffffu), hi16 = (unsigned short)(tops[i] >> 16);
+                th[(row * 4 + half) * 6 + 2 * i] = lo16 == 0x8000u ? -INFINITY : __half2float(__ushort_as_half(lo16));
+                th[(row * 4 + half) * 6 + 2 * i + 1] = hi16 == 0x8000u ? -INFINITY : __half2float(__ushort_as_half(hi16));
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (half == 0 && q < n_q) {
+                constexpr int kMerged = 24;
+                float tm[kMerged];
+#pragma unroll
+                for (int i = 0; i < kMerged; ++i) tm[i] = -INFINITY;
+                for (int i = 0; i < kMerged; ++i) {
+                    const float x = th[row * 24 + i];
+                    if (x > tm[kMerged - 1]) insert_desc(tm, x);
+                }
+                float tsel = tm[0];
+#pragma unroll
+                for (int i = 1; i < kMerged; ++i) tsel = (i == a.theta_rank - 1) ? tm[i] : tsel;
+                int hi_rank = a.hi_rank - 1;
+                hi_rank = hi_rank < 0 ? 0 : hi_rank > kTheta - 1 ? kTheta - 1 : hi_rank;
+                float thi = tm[0];
+#pragma unroll
+                for (int i = 1; i < kTheta; ++i) thi = i == hi_rank ? tm[i] : thi;
+                a.theta[q] = live ? tsel : INFINITY;           // +inf for pruned rows, -inf if the sample was too small
+                a.theta_hi[q] = live ? thi : INFINITY;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1690,6 +1748,7 @@ constexpr int kCollectCapWide = 320;          // the same for top_k > 32 (theta 
 constexpr long long kFastMinDomains = 1 << 16; // below this the sample is too small for a useful threshold
 constexpr double kFailWeight = 2.5;           // route choice: passes' worth of second chance per fraction of queries without room
 constexpr int kSampleStride = 16;             // pass 1 looks at every 16th domain
+constexpr bool kDefaultTheta16 = true;        // threshold pass through collect_hi_kernel<true> (fp16 accumulators, chunk maxima)
 constexpr bool kDefaultAcc16 = true;          // half-precision accumulators in the hi*hi-only collect pass (FWAV_UMMA_ACC16=0: off)
 constexpr long long kBatchQueries = 1 << 20;  // queries per fast-path batch (bounds the candidate buffers: 3 GB)
 
@@ -1710,9 +1769,10 @@ int launch_scan(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long sp
 }
 
 // the four-issuer hi*hi-only collect pass: one CTA per 128 queries and table share
+template <bool THETA = false>
 int launch_collect_hi(fwav_ctx *ctx, const ScanArgs &a, long long groups, long long split, cudaStream_t st) {
-    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_hi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHiSmem));
-    collect_hi_kernel<<<(unsigned)(groups * split), kHiThreads, kHiSmem, st>>>(a);
+    FWAV_CUDA(ctx, cudaFuncSetAttribute(collect_hi_kernel<THETA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHiSmem));
+    collect_hi_kernel<THETA><<<(unsigned)(groups * split), kHiThreads, kHiSmem, st>>>(a);
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;
 }
@@ -1938,7 +1998,13 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     // 1e-5 for (32; 1/32, 8) -- a handful of second chances per half million queries -- and 5e-8 for (64; 1/16, 18).
     // Fewer candidates do not pay for top_k <= 32: they leave too little room between the top_k-th score and theta
     // for the hi*hi-only collect pass (config 2 at 16 x 12: 1 % of the queries under 4e-3).
-    int theta_rank = top_k > 32 ? 18 : kTheta / 2;
+    // threshold pass through collect_hi_kernel<true> (fp16 accumulators, chunk maxima) where the CTAs run on their own and
+    // the table is not compact; its r-th largest chunk maximum sits a little below the r-th largest sampled score, so
+    // rank 7 there collects what rank 8 collects with scan_kernel (config 2: 53.2 ms per search against 54.3 at rank 8)
+    const char *theta16_env = getenv("FWAV_UMMA_THETA16");      // 0: float32 accumulators (scan_kernel<MODE_THETA>)
+    const bool theta16 = single && !compact && !dbg && !getenv("FWAV_UMMA_THETA_FULL") &&
+                         (theta16_env ? atoi(theta16_env) != 0 : kDefaultTheta16);
+    int theta_rank = top_k > 32 ? 18 : theta16 ? 7 : kTheta / 2;
     if (const char *rank_env = getenv("FWAV_UMMA_RANK")) {     // tuning knob: 16 x rank candidates expected per query
         const int v = atoi(rank_env);
         if (v >= 1 && v <= 4 * kThetaPart) theta_rank = v;
@@ -1964,6 +2030,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                   // (on its own CTA the threshold pass takes the hi*hi term alone: a threshold is an estimate anyway, and
                   // the proof of a query never relies on how it was obtained; FWAV_UMMA_THETA_FULL=1: the full split)
                   : single ? (getenv("FWAV_UMMA_THETA_FULL") ? launch_scan<MODE_THETA, false, 1>(ctx, a, groups, 1, st)
+                              : theta16 ? launch_collect_hi<true>(ctx, a, groups, 1, st)
                                                              : launch_scan<MODE_THETA, true, 1>(ctx, a, groups, 1, st))
                            : launch_scan<MODE_THETA, false, 2>(ctx, a, groups, 1, st)))
             return rc;
