@@ -5,7 +5,7 @@
 //
 // One warp per range, one lane per candidate (32 candidates per pass).  A lane
 // gathers its candidate's domain row (N floats, one or a few 16-byte loads),
-// fits both orientations with fwm::affine_fit — numpy's float32 operation
+// fits both orientations with fwm::affine_fit_pair — numpy's float32 operation
 // order, so s, o and err are the reference's bits — and the warp takes the
 // first minimum over [plain 0..K-1, mirrored 0..K-1] with a shuffle argmin
 // keyed on (err, position).
@@ -56,6 +56,15 @@ affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
             else return __ldg(rp + k);
         };
         const float r_mean = fwm::range_mean<NT>(r, N);
+        float rcreg[NT > 0 ? NT : 1];                                  // r - mean(r), once per range (:791)
+        if constexpr (NT > 0) {
+#pragma unroll
+            for (int k = 0; k < NT; ++k) rcreg[k] = npm::sub(rreg[k], r_mean);
+        }
+        auto rc = [&](int k) {
+            if constexpr (NT > 0) return rcreg[k];
+            else return npm::sub(__ldg(rp + k), r_mean);
+        };
 
         Best best{INFINITY, 0x7fffffff, 0.0f, 0.0f, 0};
         for (int c0 = 0; c0 < K; c0 += 32) {
@@ -77,12 +86,10 @@ affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
                     if constexpr (NT > 0) return treg[k];
                     else return __ldg(tp + k);
                 };
-                auto mirrored = [&](int k) {
-                    if constexpr (NT > 0) return treg[NT - 1 - k];
-                    else return __ldg(tp + (N - 1 - k));
-                };
-                fwm::Fit f0 = fwm::affine_fit<NT>(r, r_mean, plain, N);
-                fwm::Fit f1 = fwm::affine_fit<NT>(r, r_mean, mirrored, N);
+                // both orientations; for N = 8 / 16 the tile's mean, centred values and sum of squares are shared
+                // (mirroring cannot change numpy's pairwise sums there: fwm::affine_fit_pair)
+                fwm::Fit f0, f1;
+                fwm::affine_fit_pair<NT>(r, rc, r_mean, plain, N, f0, f1);
                 if (raw < 0) { f0.err = INFINITY; f1.err = INFINITY; }  // :816-817
                 if (better(f0.err, c, best.err, best.pos)) best = Best{f0.err, c, f0.s, f0.o, d};
                 if (better(f1.err, K + c, best.err, best.pos)) best = Best{f1.err, K + c, f1.s, f1.o, d};

@@ -288,6 +288,14 @@ int fwav_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int range_size,
     return fwav_launch_embed(ctx, d_rows, rows, range_size, emb_dim, d_emb, fwav_stream(ctx, stream));
 }
 
+int fwav_build_tables(fwav_ctx *ctx, const float *d_signal, int64_t n_samples, int tile_size, int range_size,
+                      int domain_step, int emb_dim, float *d_domains, float *d_emb, void *stream) {
+    FWAV_ENTER(ctx);
+    FWAV_REQUIRE(ctx, d_signal && d_domains && d_emb, "null buffer");
+    return fwav_launch_tables(ctx, d_signal, n_samples, tile_size, range_size, domain_step, emb_dim, d_domains, d_emb,
+                              fwav_stream(ctx, stream));
+}
+
 int fwav_range_activity(fwav_ctx *ctx, const float *d_ranges, int64_t n_ranges, int range_size,
                         double energy_thresh, int fast_mode, uint8_t *d_active, void *stream) {
     FWAV_ENTER(ctx);
@@ -416,8 +424,7 @@ int fwav_compress_device(fwav_ctx *ctx, const float *d_signal, int64_t n_samples
                      (long long)n_dom);
     int rc;
     if (build) {
-        if ((rc = fwav_launch_domains(ctx, d_signal, n_samples, tile_size, N, ds, d_domains, st))) return rc;
-        if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return rc;
+        if ((rc = fwav_launch_tables(ctx, d_signal, n_samples, tile_size, N, ds, emb_dim, d_domains, d_emb, st))) return rc;
     }
     if (n_ranges == 0) return FWAV_OK;
     uint8_t *d_active = nullptr;
@@ -474,9 +481,9 @@ static int compress_host_impl(fwav_ctx *ctx, const float *h_signal, int64_t n_sa
     if (!ctx->copy_stream) FWAV_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->copy_event) FWAV_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
     if ((rc = upload(ctx, d_signal, h_signal, sizeof(float) * (size_t)n_samples, st))) return rc;
-    // The tables are built first; the domain table (the .fwav payload, the largest transfer of the call) then
-    // travels to the host on the copy stream while the pre-step and the search run on the compute stream.
-    if ((rc = fwav_launch_domains(ctx, d_signal, n_samples, tile_size, N, ds, d_domains, st))) return rc;
+    // The tables (domains and embeddings, one fused pass) are built first; the domain table (the .fwav payload, the
+    // largest transfer of the call) then travels to the host on the copy stream while the pre-step and the search run on the compute stream.
+    if ((rc = fwav_launch_tables(ctx, d_signal, n_samples, tile_size, N, ds, emb_dim, d_domains, d_emb, st))) return rc;
     FWAV_CUDA(ctx, cudaEventRecord(ctx->copy_event, st));
     if (h_ranges_in) {
         if ((rc = upload(ctx, d_ranges, h_ranges_in, sizeof(float) * nr * N, st))) return rc;
@@ -515,7 +522,6 @@ static int compress_host_impl(fwav_ctx *ctx, const float *h_signal, int64_t n_sa
             code = fwav_set_error(ctx, FWAV_ERR_CUDA, "download of the domain table failed: %s", cudaGetErrorString(e));
         return code;
     };
-    if ((rc = fwav_launch_embed(ctx, d_domains, n_dom, N, emb_dim, d_emb, st))) return finish(rc);
     rc = fwav_compress_device(ctx, d_signal, n_samples, d_ranges, n_ranges, 0, tile_size, emb_dim, top_k,
                               energy_thresh, fast_mode, query_mode, 0, d_domains, d_emb, d_idx, d_s, d_o,
                               d_sym, d_err, st);

@@ -90,6 +90,11 @@ static inline cudaStream_t fwav_stream(fwav_ctx *ctx, void *stream) {
 // internal launchers (one per .cu file)
 int fwav_launch_domains(fwav_ctx *ctx, const float *d_signal, int64_t n, int tile, int N, int ds,
                         float *d_domains, cudaStream_t st);
+int fwav_launch_half_sums(fwav_ctx *ctx, const float *d_signal, int64_t n, int64_t n_half, int stride, float *d_half,
+                          cudaStream_t st);
+// domains + embeddings in one pass where the geometry allows (tables.cu), else the two launchers below
+int fwav_launch_tables(fwav_ctx *ctx, const float *d_signal, int64_t n, int tile, int N, int ds, int emb_dim,
+                       float *d_domains, float *d_emb, cudaStream_t st);
 int fwav_launch_prestep(fwav_ctx *ctx, const float *d_signal, int64_t n, int N, double energy_thresh, float *d_ranges,
                         double *d_sumsq, cudaStream_t st);
 int fwav_launch_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int N, int emb_dim,

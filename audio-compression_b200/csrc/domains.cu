@@ -10,45 +10,14 @@
 // Fast path (run == 256, i.e. every tile_size that is a multiple of 256 and
 // >= 1024): numpy reduces 256 = leaf(128) + leaf(128) and a leaf depends only on
 // where it starts, so the 128-sample "half sums" are computed once per start
-// position (n/gcd(ds,128) of them, 128 adds each) and every output is one add of
-// two half sums and a divide.  That is ~32x fewer adds than summing per output
-// and turns the kernel pair into a streaming, HBM/L2-bound pass:
+// position (n/gcd(ds,128) of them; tables.cu builds them from shared chains, 15 adds
+// per sample) and every output is one add of two half sums and a divide.  That
+// turns the kernel pair into a streaming, HBM/L2-bound pass:
 //   algorithmic bytes = 4*n read + 4*range_size*n_domains written.
 #include "common.cuh"
 #include "fwav_math.cuh"
 
 namespace {
-
-__global__ void __launch_bounds__(256)
-half_sums_kernel(const float *__restrict__ signal, long long n_half, int stride,
-                 float *__restrict__ half) {
-    auto sig = [&](long long i) { return __ldg(signal + i); };
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_half;
-         i += (long long)gridDim.x * blockDim.x)
-        half[i] = fwm::half_sum128(sig, i * stride);
-}
-
-// stride % 4 == 0 (domain_step a multiple of 4): every leaf starts on a 16-byte boundary, so the 128 samples are
-// 32 aligned float4 loads (a warp's load covers 512 contiguous bytes) instead of 128 scalar loads 16 bytes apart.
-// Same eight strided accumulators, same order of additions as npm::pairwise_leaf.
-__global__ void __launch_bounds__(256)
-half_sums_vec4_kernel(const float *__restrict__ signal, long long n_half, int stride,
-                      float *__restrict__ half) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_half;
-         i += (long long)gridDim.x * blockDim.x) {
-        const float4 *p = reinterpret_cast<const float4 *>(signal + i * stride);
-        float4 a = __ldg(p), b = __ldg(p + 1);
-        float r0 = a.x, r1 = a.y, r2 = a.z, r3 = a.w, r4 = b.x, r5 = b.y, r6 = b.z, r7 = b.w;
-#pragma unroll
-        for (int m = 1; m < 16; ++m) {
-            a = __ldg(p + 2 * m);
-            b = __ldg(p + 2 * m + 1);
-            r0 = npm::add(r0, a.x); r1 = npm::add(r1, a.y); r2 = npm::add(r2, a.z); r3 = npm::add(r3, a.w);
-            r4 = npm::add(r4, b.x); r5 = npm::add(r5, b.y); r6 = npm::add(r6, b.z); r7 = npm::add(r7, b.w);
-        }
-        half[i] = npm::add(npm::add(npm::add(r0, r1), npm::add(r2, r3)), npm::add(npm::add(r4, r5), npm::add(r6, r7)));
-    }
-}
 
 // N == 16, run == 256: a block builds 256 consecutive domains per pass.  Column k of those rows needs the half
 // sums at (j*ds + k*256) / stride and + 128 / stride for 256 consecutive j: contiguous reads per k; the 256 x 16
@@ -164,12 +133,7 @@ int fwav_launch_domains(fwav_ctx *ctx, const float *d_signal, int64_t n, int til
         float *d_half = nullptr;
         int rc = fwav_ws_reserve(ctx, WS_HALF, sizeof(float) * (size_t)n_half, (void **)&d_half);
         if (rc) return rc;
-        const bool sig16 = (reinterpret_cast<uintptr_t>(d_signal) & 15) == 0;
-        if (stride % 4 == 0 && sig16)
-            half_sums_vec4_kernel<<<grid_for(n_half, 256, ctx->num_sms, 8), 256, 0, st>>>(d_signal, n_half, stride, d_half);
-        else
-            half_sums_kernel<<<grid_for(n_half, 256, ctx->num_sms, 8), 256, 0, st>>>(d_signal, n_half, stride, d_half);
-        FWAV_LAUNCH_CHECK(ctx);
+        if ((rc = fwav_launch_half_sums(ctx, d_signal, n, n_half, stride, d_half, st))) return rc;
         if (N == 16 && (reinterpret_cast<uintptr_t>(d_domains) & 15) == 0)
             domains_from_halves_t16_kernel<<<grid_for(n_dom, 256, ctx->num_sms, 8), 256, 0, st>>>(
                 d_half, n_dom, ds, stride, d_domains);

@@ -13,62 +13,12 @@
 // HBM traffic per row: 4*N bytes read + 4*emb_dim bytes written (streaming).
 #include "common.cuh"
 #include "fwav_math.cuh"
+#include "embed_static.cuh"
 
 namespace {
 
 template <int N, int HALF>
-struct TablesP {
-    double tonal[HALF * N];
-    double transient[HALF * N];
-    double w[N];
-};
-
-// Same arithmetic, in the same order, as fwm::embed_row; fully unrolled so the
-// coefficients are constant-bank operands.
-template <int N, int HALF>
-__device__ __forceinline__ void embed_row_static(const float (&x)[N], const TablesP<N, HALF> &T,
-                                                 float (&out)[2 * HALF]) {
-    double ssq = 0.0;
-#pragma unroll
-    for (int k = 0; k < HALF; ++k) {
-        double acc = 0.0;
-#pragma unroll
-        for (int n = 0; n < N; ++n) acc = fma((double)x[n], T.tonal[k * N + n], acc);
-        const float v = (float)acc;
-        out[k] = v;
-        ssq += (double)v * (double)v;
-    }
-    const float nrm = npm::sqrt((float)ssq);
-    if (nrm > 1e-8f) {
-#pragma unroll
-        for (int k = 0; k < HALF; ++k) out[k] = npm::div(out[k], nrm);
-    }
-    constexpr int LIVE = HALF < N ? HALF : N;
-    double u[N];
-    u[0] = 0.0 * T.w[0];
-#pragma unroll
-    for (int n = 1; n < N; ++n) u[n] = (double)npm::sub(x[n], x[n - 1]) * T.w[n];
-    double tv[LIVE];
-    double tsq = 0.0;
-#pragma unroll
-    for (int k = 0; k < LIVE; ++k) {
-        double acc = 0.0;
-#pragma unroll
-        for (int n = 0; n < N; ++n) acc = fma(u[n], T.transient[k * N + n], acc);
-        tv[k] = acc;
-        tsq += acc * acc;
-    }
-    const double tn = sqrt(tsq);
-#pragma unroll
-    for (int k = 0; k < HALF; ++k) {
-        float v = 0.0f;
-        if (k < LIVE) v = (float)(tn > 1e-8 ? tv[k] / tn : tv[k]);
-        out[HALF + k] = v;
-    }
-}
-
-template <int N, int HALF>
-__global__ void __launch_bounds__(128, N <= 16 ? 4 : 2)      // 12 warps per SM were not enough to hide the DFMA chains
+__global__ void __launch_bounds__(128, N <= 16 ? 4 : 2)
 embed_static_kernel(const float *__restrict__ rows, long long n_rows, float *__restrict__ emb,
                     const __grid_constant__ TablesP<N, HALF> T) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;

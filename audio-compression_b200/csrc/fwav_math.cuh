@@ -79,8 +79,21 @@ FWAV_HD float half_sum128(Sig sig, long long start) {
     auto at = [&](int i) { return sig(start + i); };
     return npm::pairwise_leaf(at, 0, 128);
 }
+// The leaf's eight strided accumulators are chains that depend on their start alone: r_i of the leaf at p is
+// c(p + i), c(q) = x[q] + x[q+8] + ... + x[q+120] added left to right, and the leaf is the tree over c(p..p+7)
+// (npm::pairwise_leaf with n = 128).  tables.cu computes every chain once and shares it between the leaves.
+template <class Sig>
+FWAV_HD float leaf_chain(Sig sig, long long q) {
+    float c = sig(q);
+    FWAV_UNROLL
+    for (int m = 1; m < 16; ++m) c = npm::add(c, sig(q + 8 * m));
+    return c;
+}
+FWAV_HD float half_from_chains(float c0, float c1, float c2, float c3, float c4, float c5, float c6, float c7) {
+    return npm::add(npm::add(npm::add(c0, c1), npm::add(c2, c3)), npm::add(npm::add(c4, c5), npm::add(c6, c7)));
+}
 FWAV_HD float domain_from_halves(float h0, float h1) {
-    return npm::div(npm::add(0.0f, npm::add(h0, h1)), 256.0f);
+    return npm::mul(npm::add(0.0f, npm::add(h0, h1)), 1.0f / 256.0f);      // == / 256 exactly (a power of two)
 }
 
 // ---------------------------------------------------------------------------
@@ -202,6 +215,45 @@ FWAV_HD Fit affine_fit(RowR r, float r_mean, RowT t, int N) {
     };
     f.err = npm::sqrt(npm::sum_n<NS>(resid, N));                                  // :813
     return f;
+}
+
+// Both orientations of one candidate tile (plain, then mirrored: t(N-1-i)) in one go.  rc(i) = r(i) - r_mean is the
+// caller's (once per range).  For N = 8 and N = 16 numpy's pairwise sum of the mirrored row adds the same pairs as
+// that of the plain row -- the eight accumulators swap places (r'_j = r_(7-j)) and every level of the combining tree
+// only sees its two operands exchanged, which IEEE addition does not notice -- so the tile's mean, its centred
+// values and its sum of squares are computed once and serve both fits: the same bits as two affine_fit calls with a
+// quarter of the work removed.  Other sizes (N = 4: a left-to-right sum; N = 32: four-term chains per accumulator)
+// round differently when mirrored and take the two calls.
+template <int NS = 0, class RowR, class RowC, class RowT>
+FWAV_HD void affine_fit_pair(RowR r, RowC rc, float r_mean, RowT t, int N, Fit &plain, Fit &mirr) {
+    if constexpr (NS == 8 || NS == 16) {
+        const float d_mean = npm::mean_n<NS>(t, N);                                // :796 (both orientations)
+        float dc[NS];
+        FWAV_UNROLL
+        for (int i = 0; i < NS; ++i) dc[i] = npm::sub(t(i), d_mean);               // :797
+        auto self = [&](int i) { return npm::mul(dc[i], dc[i]); };
+        const float den = npm::add(npm::sum_n<NS>(self, N), 1e-12f);              // :803
+        auto finish = [&](float num, auto tt, Fit &f) {
+            f.s = npm::div(num, den);                                              // :804
+            f.o = npm::sub(r_mean, npm::mul(f.s, d_mean));                         // :805
+            const float s = f.s, o = f.o;
+            auto resid = [&](int i) {                                              // :811-812
+                float v = npm::sub(npm::add(npm::mul(s, tt(i)), o), r(i));
+                return npm::mul(v, v);
+            };
+            f.err = npm::sqrt(npm::sum_n<NS>(resid, N));                          // :813
+        };
+        auto cross0 = [&](int i) { return npm::mul(dc[i], rc(i)); };
+        auto cross1 = [&](int i) { return npm::mul(dc[NS - 1 - i], rc(i)); };
+        auto t1 = [&](int i) { return t(NS - 1 - i); };
+        finish(npm::sum_n<NS>(cross0, N), t, plain);                               // :802
+        finish(npm::sum_n<NS>(cross1, N), t1, mirr);
+    } else {
+        const int n_run = NS > 0 ? NS : N;
+        auto t1 = [&](int i) { return t(n_run - 1 - i); };
+        plain = affine_fit<NS>(r, r_mean, t, N);
+        mirr = affine_fit<NS>(r, r_mean, t1, N);
+    }
 }
 
 FWAV_HD float clip(float v, float lo, float hi) {   // np.clip

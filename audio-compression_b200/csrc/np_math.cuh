@@ -152,9 +152,12 @@ FWAV_HD float sum_n(F at, int n) {
     if constexpr (NS > 0) return add(0.0f, pairwise_static<0, NS>(at));
     else return np_sum<2>(at, n);
 }
+// (a count that is a power of two divides exactly like the multiplication by its reciprocal: both round the same
+// real number once, subnormal results included -- and the multiplication is one instruction, not a division sequence)
 template <int NS, class F>
 FWAV_HD float mean_n(F at, int n) {
-    if constexpr (NS > 0) return div(sum_n<NS>(at, n), (float)NS);
+    if constexpr (NS > 0 && (NS & (NS - 1)) == 0) return mul(sum_n<NS>(at, n), 1.0f / (float)NS);
+    else if constexpr (NS > 0) return div(sum_n<NS>(at, n), (float)NS);
     else return div(sum_n<0>(at, n), (float)n);
 }
 

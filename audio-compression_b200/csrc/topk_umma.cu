@@ -123,6 +123,11 @@ struct ScanArgs {
     // MODE_LISTS: rows whose kept lists cannot PROVE the top_k (see lists_unsafe) are appended here for the FFMA kernel
     int *lfail_list, *lfail_count;
     const unsigned *norms;     // largest squared row norms (row_norm2_max_kernel): the error bound of the filter scores
+    // collect_hi_kernel: where in the table the CTAs of this launch currently are (stage index relative to the split's
+    // first stage).  A CTA starts its lap where the others are and publishes its own position now and then, so that
+    // the 148 resident CTAs stream the SAME part of the 63 MB table at any time and L2 serves all but the first
+    // touch (NULL: every CTA starts at a position derived from its queries).
+    int *front;
 };
 
 
@@ -1260,13 +1265,18 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    int *front_slot = reinterpret_cast<int *>(tmem_slot + 1);
+    if (threadIdx.x == 32) *front_slot = a.front ? *reinterpret_cast<volatile int *>(a.front + split) : -1;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int s_lo = (int)((long long)split * a.n_stages / a.n_split), s_hi = (int)((long long)(split + 1) * a.n_stages / a.n_split);
     const int n_visit = s_hi - s_lo;
-    const int t_first = s_lo + (int)((q_base / kDStage) % n_visit);
+    // any starting stage is valid (every CTA visits all n_visit stages of its split, wrapping; the order in which a
+    // query's candidates are collected does not matter to finalize_kernel): start where the other CTAs are
+    const int front0 = *front_slot;
+    const int t_first = s_lo + (front0 >= 0 ? front0 % n_visit : (int)((q_base / kDStage) % n_visit));
 
     if (warp >= 16) {
         // ===== issuer + producer warps: warp i owns the stages t = i (mod 4) and their ring slots i, i + 4 =====
@@ -1299,6 +1309,11 @@ __global__ void __launch_bounds__(kHiThreads, 1) collect_hi_kernel(const ScanArg
         int k = 0;
         for (int t = i; t < n_visit; t += kHiIss, ++k) {
             if (lane == 0) FWAV_HI_TRACE(0, t);
+            if (i == 0 && (k & 7) == 0 && a.front && elect_one()) {       // every 32nd stage: where this CTA is
+                int rel = t_first - s_lo + t;
+                if (rel >= n_visit) rel -= n_visit;
+                *reinterpret_cast<volatile int *>(a.front + split) = rel;
+            }
             const int tn = t + kHiIss;
             if (tn < n_visit) {                    // next own stage: its slot was freed by this warp's own MMA of t - 4
                 mbar_wait(bar_empty + 8 * (tn & (kStages - 1)), (uint32_t)(((tn / kStages) & 1) ^ 1));
@@ -1513,7 +1528,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
     ok = ok && c <= key_cap;                           // more than the shared-memory path holds: treated as an overflow
     overflow = !ok;
     int n_sel = 0;
-    float last = -INFINITY;
+    float last = -INFINITY, first = -INFINITY;
     const int want = (long long)top_k < n_d ? top_k : (int)n_d;
     // canonical score of candidate `id` as a key (0: a padded column past the end of the table)
     float qv[ED];
@@ -1574,6 +1589,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
                 if (scores) scores[q * top_k + r] = unorder_bits((uint32_t)(best >> 32));
             }
             last = unorder_bits((uint32_t)(best >> 32));
+            if (r == 0) first = last;
             ++n_sel;
         }
         ok = n_sel == want && last >= theta[q] + slack;
@@ -1606,6 +1622,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
             }
             prev = best;
             last = unorder_bits((uint32_t)(best >> 32));
+            if (r == 0) first = last;
             ++n_sel;
         }
         ok = n_sel == want && last >= theta[q] + slack;
@@ -1621,6 +1638,14 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         // been filtered out.  Every domain that beats `last` scores at least last - slack_full on the tensor
         // cores with the full split: a second collect pass with this threshold finds them all and verifies.
         if (theta_retry && !overflow && n_sel == want && want > 0) theta_retry[q] = fminf(theta[q], last - 2.0f * slack_full);
+        // "short": fewer than top_k domains reach theta at all (the tail of the sampled estimate: a handful of queries
+        // per half million).  The same threshold would fail the same way, and the exact list kernel costs ~0.8 ms
+        // however few queries it gets: the second pass has many times the buffer room, so it looks twice as far below
+        // the best score found (any threshold is valid: the proof is checked against whatever was used).
+        else if (theta_retry && !overflow && n_sel < want) {
+            const float t = theta[q];
+            theta_retry[q] = t - fmaxf(n_sel > 0 ? first - t : 0.0f, 0.02f);
+        }
     }
 }
 
@@ -1980,9 +2005,13 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
     float *d_theta = nullptr;
     int32_t *d_cbuf = nullptr;
     int *d_cnt = nullptr, *d_fail = nullptr;
-    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 8) * sizeof(float), (void **)&d_theta))) return rc;
+    if ((rc = fwav_ws_reserve(ctx, WS_UMMA_THETA, (size_t)(2 * n_q + 32) * sizeof(float), (void **)&d_theta))) return rc;
     float *d_theta_hi = d_theta + n_q;
     int *d_flat = reinterpret_cast<int *>(d_theta + 2 * n_q);
+    // collect_hi_kernel's shared table position (ScanArgs::front): one int for the main launch, one per split of the tail
+    int *d_front = d_flat + 8;
+    const char *front_env = getenv("FWAV_UMMA_FRONT");         // 0: every CTA starts at its own static position
+    const bool use_front = !(front_env && atoi(front_env) == 0);
 
     int collect_cap = top_k > 32 ? kCollectCapWide : kCollectCap;
     if (const char *cap_env = getenv("FWAV_UMMA_CAP")) {       // test knob: small buffers force the failure paths
@@ -2089,6 +2118,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
         }
         const long long main_q = tail_groups ? main_groups * kQTile : nq;
         const int tail_cap = collect_cap / 2;      // a split sees 1/tail_split of the table: ~256 / (4 * tail_split) hits per part expected
+        if (use_front && acc16) {
+            FWAV_CUDA(ctx, cudaMemsetAsync(d_front, 0, 16 * sizeof(int), st));
+            a.front = d_front;
+        }
         ScanArgs at = a;
         if (tail_groups) {
             int32_t *d_tbuf = nullptr;
@@ -2105,6 +2138,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             at.cbuf = d_tbuf;
             at.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_tbuf) + nb);
             at.cap = tail_cap;
+            if (a.front) at.front = d_front + 8;       // tail_split <= 8
         }
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;

@@ -49,6 +49,7 @@ SIGNATURES = [
     ("fwav_count_domains", i64, [i64, C.c_int, C.c_int]),
     ("fwav_build_domains", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     ("fwav_embed", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, c_ptr, c_ptr]),
+    ("fwav_build_tables", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     ("fwav_topk", C.c_int, [c_ctx, c_ptr, i64, c_ptr, i64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     ("fwav_range_activity", C.c_int, [c_ctx, c_ptr, i64, C.c_int, C.c_double, C.c_int, c_ptr, c_ptr]),
     ("fwav_affine_match", C.c_int, [c_ctx, c_ptr, i64, C.c_int, c_ptr, i64, c_ptr, C.c_int, C.c_double,
@@ -357,6 +358,11 @@ class Context:
 
     def embed(self, d_rows, rows, range_size, emb_dim, d_emb, stream=None):
         self._check(self.lib.fwav_embed(self.h, d_rows, rows, range_size, emb_dim, d_emb, stream))
+
+    def build_tables(self, d_signal, n, tile_size, range_size, domain_step, emb_dim, d_domains, d_emb, stream=None):
+        """domains + embeddings in one pass (fwav_build_tables)"""
+        self._check(self.lib.fwav_build_tables(self.h, d_signal, n, tile_size, range_size, domain_step, emb_dim,
+                                               d_domains, d_emb, stream))
 
     def range_activity(self, d_ranges, n_r, range_size, energy_thresh, fast_mode, d_active, stream=None):
         self._check(self.lib.fwav_range_activity(self.h, d_ranges, n_r, range_size, float(energy_thresh),

@@ -193,9 +193,8 @@ class CudaEngine:
     def build_tables(self, signal, tile_size, emb_dim, out=None):
         N, ds = self.lib.geometry(tile_size)
         domains, embs = out if out is not None else self.alloc_tables(signal, tile_size, emb_dim)
-        n_d = domains.shape[0]
-        self.ctx.build_domains(signal.data_ptr(), signal.shape[0], tile_size, N, ds, domains.data_ptr(), self._stream())
-        self.ctx.embed(domains.data_ptr(), n_d, N, emb_dim, embs.data_ptr(), self._stream())
+        self.ctx.build_tables(signal.data_ptr(), signal.shape[0], tile_size, N, ds, emb_dim, domains.data_ptr(),
+                              embs.data_ptr(), self._stream())
         return domains, embs
 
     def match_slice(self, ranges, lo, hi, domains, embs, tile_size, emb_dim, top_k, energy_thresh, fast_mode,

@@ -266,31 +266,29 @@ def run_ours(args):
     p = lambda t: t.data_ptr()  # noqa: E731
     rng_ptr = d_ranges.data_ptr() + lo * N * 4
 
-    stage_names = ["domains", "embed", "bcast", "activity", "topk", "affine", "gather"]
+    stage_names = ["tables", "bcast", "activity", "topk", "affine", "gather"]
 
     def step(ev):
         """One pass; ev is a list of len(stage_names)+1 CUDA events recorded between stages."""
         ev[0].record()
         if rank == 0 or not args.bcast:
-            ctx.build_domains(p(d_signal), n, tile, N, ds, p(d_domains), stream)
+            # domains + embeddings in one pass (fwav_build_tables: chain half sums, then rows built and embedded in registers)
+            ctx.build_tables(p(d_signal), n, tile, N, ds, EMB_DIM, p(d_domains), p(d_emb), stream)
         ev[1].record()
-        if rank == 0 or not args.bcast:
-            ctx.embed(p(d_domains), n_d, N, EMB_DIM, p(d_emb), stream)
-        ev[2].record()
         if world > 1 and args.bcast:
             dist.broadcast(d_domains, 0)
             dist.broadcast(d_emb, 0)
-        ev[3].record()
+        ev[2].record()
         ctx.range_activity(rng_ptr, cnt, N, ENERGY_THRESH, True, p(d_active), stream)
-        ev[4].record()
+        ev[3].record()
         ctx.topk(p(d_emb) + lo * EMB_DIM * 4, cnt, p(d_emb), n_d, EMB_DIM, K, p(d_active), p(d_cand), None, stream)
-        ev[5].record()
+        ev[4].record()
         ctx.affine_match(rng_ptr, cnt, N, p(d_domains), n_d, p(d_cand), K, 16.0,
                          p(d_m32[0]), p(d_m32[1]), p(d_m32[2]), p(d_m32[4]), p(d_m32[3]), stream)
-        ev[6].record()
+        ev[5].record()
         if world > 1:
             dist.all_gather_into_tensor(g_m32, d_m32)
-        ev[7].record()
+        ev[6].record()
 
     def barrier():
         torch.cuda.synchronize()
@@ -489,7 +487,8 @@ def run_ours(args):
     roof["ms_per_launch"] = topk_ms_roof if tensor else topk_ms
     hbm = peaks["hbm_gbs"]
     kern = {}
-    for name, byts in (("domains", 4.0 * n + 4.0 * N * n_d), ("embed", 4.0 * (N + EMB_DIM) * n_d),
+    # tables: the signal read once, both tables written once (the domain rows are embedded in registers)
+    for name, byts in (("tables", 4.0 * n + 4.0 * (N + EMB_DIM) * n_d),
                        ("affine", (K * N * 4 + N * 4 + K * 4 + 17.0) * n_r / world)):
         ms = float(per_stage[stage_names.index(name)])
         kern[name] = {"ms": ms, "bound": "hbm", "achieved": byts / (ms * 1e-3) / 1e9 if ms > 0 else None,

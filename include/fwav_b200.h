@@ -109,6 +109,14 @@ int fwav_build_domains(fwav_ctx *ctx, const float *d_signal, int64_t n_samples,
 int fwav_embed(fwav_ctx *ctx, const float *d_rows, int64_t rows, int range_size,
                int emb_dim, float *d_emb, void *stream);
 
+/* A1 + A3 in one pass — replaces build_domains_memmap (fractal.py:285-334) followed by
+ * build_domain_embeddings (:238-280, the pass that re-reads the memmap row by row).  Same outputs, bit for bit, as
+ * fwav_build_domains + fwav_embed; for the geometries compress_audio derives from a tile_size that is a multiple
+ * of 256 (range_size 4 / 8 / 16 / 32, domain_step = range_size / 4) with the two-head embedding at emb_dim 16 the
+ * domain rows never leave the registers between the two steps (the table is written once and not read back). */
+int fwav_build_tables(fwav_ctx *ctx, const float *d_signal, int64_t n_samples, int tile_size, int range_size,
+                      int domain_step, int emb_dim, float *d_domains, float *d_emb, void *stream);
+
 /* A4/A5 — replaces cpu_worker's linear search + pad_candidates
  * (fractal.py:535-552, 598-623) for all queries at once.
  * d_cand is (n_queries, top_k) int32: indices of the top_k largest

@@ -7,6 +7,12 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "lts__t_sector_hit_rate.pct", "lts__t_sector_op_read_hit_rate.pct", "lts__t_sector_op_write_hit_rate.pct",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum", "lts__t_sectors_srcunit_tex_op_write_lookup_miss.sum",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active",
         "sm__cycles_active.avg", "launch__registers_per_thread", "launch__block_size", "launch__grid_size",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",

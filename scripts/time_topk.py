@@ -18,8 +18,7 @@ st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 d_sig = torch.from_numpy(sig).to(dev)
 d_dom = torch.empty((n_d, N), device=dev); d_emb = torch.empty((n_d, ED), device=dev)
 d_cand = torch.empty((n_q, K), dtype=torch.int32, device=dev)
-ctx.build_domains(d_sig.data_ptr(), len(sig), tile, N, ds, d_dom.data_ptr(), st.cuda_stream)
-ctx.embed(d_dom.data_ptr(), n_d, N, ED, d_emb.data_ptr(), st.cuda_stream)
+ctx.build_tables(d_sig.data_ptr(), len(sig), tile, N, ds, ED, d_dom.data_ptr(), d_emb.data_ptr(), st.cuda_stream)
 ms = []
 for r in range(reps + 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,6 +27,6 @@ for r in range(reps + 1):
     e1.record(); torch.cuda.synchronize()
     if r: ms.append(e0.elapsed_time(e1))
 pairs = float(n_q) * n_d
-print(json.dumps(dict(fallbacks=ctx.search_fallbacks(), phases={k: round(v, 3) for k, v in ctx.search_timings().items()}, rank=os.environ.get('FWAV_UMMA_RANK', 'default'), reps=reps + 1, impl=impl, dbg=os.environ.get("FWAV_UMMA_DEBUG", "0"), scale=scale, n_q=n_q, n_d=n_d,
+print(json.dumps(dict(fallbacks=ctx.search_fallbacks(), phases={k: round(v, 3) for k, v in ctx.search_timings().items()}, rank=os.environ.get('FWAV_UMMA_RANK', 'default'), front=os.environ.get('FWAV_UMMA_FRONT', 'default'), reps=reps + 1, impl=impl, dbg=os.environ.get("FWAV_UMMA_DEBUG", "0"), scale=scale, n_q=n_q, n_d=n_d,
                       ms=float(np.mean(ms)), gpairs_per_s=pairs / np.mean(ms) / 1e6,
                       cycles_per_tilestep_per_sm=np.mean(ms) * 1e-3 * 1.965e9 / (((n_q + 255) // 256) * ((n_d + 127) // 128) / 148))))

@@ -10,6 +10,7 @@
 
 #include "fwav_math.cuh"
 #include "embed_tables.h"
+#include "tables_geom.h"
 
 template <int NS, class R, class T>
 static fwm::Fit fit_dispatch(R r, float r_mean, T t, int N) {
@@ -17,6 +18,40 @@ static fwm::Fit fit_dispatch(R r, float r_mean, T t, int N) {
 }
 #define HH_BY_N(N, CALL)                        \
     ((N) == 4 ? CALL(4) : (N) == 8 ? CALL(8) : (N) == 16 ? CALL(16) : (N) == 32 ? CALL(32) : CALL(0))
+
+// the kernel's own form: both orientations of a candidate through fwm::affine_fit_pair (shared tile statistics for
+// N = 8 / 16), first minimum over [plain 0..K-1, mirrored 0..K-1]
+template <int NS>
+static void affine_pair_rows(const float *ranges, long long n_r, int N, const float *domains, const int32_t *cand, int K,
+                             float clipf, int32_t *idx, float *s, float *o, uint8_t *sym, float *err) {
+    for (long long i = 0; i < n_r; ++i) {
+        const float *r = ranges + i * N;
+        auto rr = [&](int k) { return r[k]; };
+        const float r_mean = fwm::range_mean<NS>(rr, N);
+        auto rc = [&](int k) { return npm::sub(r[k], r_mean); };
+        float best = std::numeric_limits<float>::infinity();
+        int best_pos = -1;
+        fwm::Fit best_fit{0, 0, 0};
+        std::vector<fwm::Fit> f0(K), f1(K);
+        for (int c = 0; c < K; ++c) {
+            const int raw = cand[i * K + c];
+            const float *t = domains + (long long)(raw < 0 ? 0 : raw) * N;
+            auto tt = [&](int k) { return t[k]; };
+            fwm::affine_fit_pair<NS>(rr, rc, r_mean, tt, N, f0[c], f1[c]);
+            if (raw < 0) f0[c].err = f1[c].err = std::numeric_limits<float>::infinity();
+        }
+        for (int pos = 0; pos < 2 * K; ++pos) {
+            const fwm::Fit &f = pos < K ? f0[pos] : f1[pos - K];
+            if (best_pos < 0 || f.err < best) { best = f.err; best_pos = pos; best_fit = f; }
+        }
+        const int raw = cand[i * K + best_pos % K];
+        idx[i] = raw < 0 ? 0 : raw;
+        s[i] = fwm::clip(best_fit.s, -clipf, clipf);
+        o[i] = best_fit.o;
+        sym[i] = best_pos >= K;
+        err[i] = best_fit.err;
+    }
+}
 
 extern "C" {
 
@@ -38,6 +73,47 @@ void hh_build_domains(const float *sig, long long n, int tile, int N, int ds, fl
             else
                 out[j * N + k] = fwm::domain_value(s, start, run);
         }
+}
+
+// CPU emulation of tables.cu, block by block and thread by thread with the kernels' own index arithmetic:
+// half_sums_chain_kernel (staged samples, 17 chains per thread, leaves from eight chains) ...
+void hh_half_sums_chain(const float *sig, long long n, long long n_half, int stride, float *half) {
+    if (n_half <= 0) return;
+    const long long blocks = ((n_half - 1) * stride) / kChainOut + 1;
+    std::vector<float> xs(kChainX), cs(kChainP);
+    for (long long b = 0; b < blocks; ++b) {
+        const long long Q0 = b * kChainOut;
+        for (int i = 0; i < kChainX; ++i) xs[i] = Q0 + i < n ? sig[Q0 + i] : 0.0f;
+        for (int tid = 0; tid < kChainThreads; ++tid) {
+            const int base = (tid & 7) + 8 * kChainT * (tid >> 3);
+            float v[kChainT + 15];
+            for (int i = 0; i < kChainT + 15; ++i) v[i] = xs[base + 8 * i];
+            for (int i = 0; i < kChainT; ++i) {
+                float c = v[i];
+                for (int m = 1; m < 16; ++m) c = npm::add(c, v[i + m]);
+                cs[base + 8 * i] = c;
+            }
+        }
+        const long long u_lo = (Q0 + stride - 1) / stride;
+        long long u_hi = (Q0 + kChainOut + stride - 1) / stride;
+        if (u_hi > n_half) u_hi = n_half;
+        for (long long u = u_lo; u < u_hi; ++u) {
+            const int p = (int)(u * stride - Q0);
+            half[u] = fwm::half_from_chains(cs[p], cs[p + 1], cs[p + 2], cs[p + 3], cs[p + 4], cs[p + 5], cs[p + 6], cs[p + 7]);
+        }
+    }
+}
+
+// ... and the domain rows of tables_from_halves_kernel<N, DS> (window of half sums per pass of kTabJ domains)
+void hh_domains_from_halves(const float *half, long long n_half, long long n_dom, int N, int DS, float *out) {
+    const int KS = 256 / DS, HS = 128 / DS, W = kTabJ + (N * 256 - 128) / DS;
+    std::vector<float> hs(W);
+    for (long long j0 = 0; j0 < n_dom; j0 += kTabJ) {
+        for (int i = 0; i < W; ++i) hs[i] = j0 + i < n_half ? half[j0 + i] : 0.0f;
+        for (int jl = 0; jl < kTabJ && j0 + jl < n_dom; ++jl)
+            for (int k = 0; k < N; ++k)
+                out[(j0 + jl) * N + k] = fwm::domain_from_halves(hs[jl + k * KS], hs[jl + k * KS + HS]);
+    }
 }
 
 void hh_embed(const float *rows, long long n_rows, int N, int emb_dim, float *out) {
@@ -106,6 +182,13 @@ void hh_affine(const float *ranges, long long n_r, int N, const float *domains, 
         sym[i] = best_pos >= K;
         err[i] = best_fit.err;
     }
+}
+
+void hh_affine_pair(const float *ranges, long long n_r, int N, const float *domains, const int32_t *cand, int K,
+                    double s_clip, int32_t *idx, float *s, float *o, uint8_t *sym, float *err) {
+    const float clipf = (float)std::fabs(s_clip);
+#define HH_PAIR(NS) affine_pair_rows<NS>(ranges, n_r, N, domains, cand, K, clipf, idx, s, o, sym, err)
+    if (N == 4) HH_PAIR(4); else if (N == 8) HH_PAIR(8); else if (N == 16) HH_PAIR(16); else if (N == 32) HH_PAIR(32); else HH_PAIR(0);
 }
 
 // full decoder loop on the CPU with the device's per-range function

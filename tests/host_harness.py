@@ -17,7 +17,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [SRC] + [os.path.join(INC, f) for f in ("np_math.cuh", "fwav_math.cuh", "embed_tables.h")]
+    deps = [SRC] + [os.path.join(INC, f) for f in ("np_math.cuh", "fwav_math.cuh", "embed_tables.h", "tables_geom.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -71,6 +71,18 @@ class Harness:
                                   _p(out), C.c_int(int(force_generic)))
         return out
 
+    def build_domains_chain(self, sig, tile, N, ds):
+        """the route of tables.cu: chain half sums at every ds-th sample, domain rows from a staged window"""
+        sig = f32(sig)
+        n = len(sig)
+        nd = 0 if n < tile else (n - tile) // ds + 1
+        n_half = (n - 128) // ds + 1
+        half = np.full(max(n_half, 1), np.nan, np.float32)
+        self.lib.hh_half_sums_chain(_p(sig), C.c_longlong(n), C.c_longlong(n_half), C.c_int(ds), _p(half))
+        out = np.empty((nd, N), np.float32)
+        self.lib.hh_domains_from_halves(_p(half), C.c_longlong(n_half), C.c_longlong(nd), C.c_int(N), C.c_int(ds), _p(out))
+        return out, half
+
     def embed(self, rows, emb_dim=16):
         rows = f32(rows)
         out = np.empty((rows.shape[0], emb_dim), np.float32)
@@ -84,13 +96,14 @@ class Harness:
                              C.c_double(thr), C.c_int(int(fast)), _p(out))
         return out
 
-    def affine(self, ranges, domains, cand, s_clip=16.0):
+    def affine(self, ranges, domains, cand, s_clip=16.0, pair=False):
+        """pair=True: the kernel's form (fwm::affine_fit_pair: tile statistics shared between the orientations)"""
         ranges, domains = f32(ranges), f32(domains)
         cand = np.ascontiguousarray(cand, np.int32)
         n = ranges.shape[0]
         idx = np.empty(n, np.int32); s = np.empty(n, np.float32); o = np.empty(n, np.float32)
         sym = np.empty(n, np.uint8); err = np.empty(n, np.float32)
-        self.lib.hh_affine(_p(ranges), C.c_longlong(n), C.c_int(ranges.shape[1]), _p(domains), _p(cand),
+        (self.lib.hh_affine_pair if pair else self.lib.hh_affine)(_p(ranges), C.c_longlong(n), C.c_int(ranges.shape[1]), _p(domains), _p(cand),
                            C.c_int(cand.shape[1]), C.c_double(s_clip), _p(idx), _p(s), _p(o), _p(sym), _p(err))
         return dict(idx=idx, s=s, o=o, sym=sym, err=err)
 

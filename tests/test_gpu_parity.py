@@ -68,6 +68,50 @@ def test_embeddings_close(ctx, name):
     assert np.array_equal((got == 0).all(axis=0), (g["embeddings"] == 0).all(axis=0))   # padding layout
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_tables_in_one_pass_bit_exact(ctx, name):
+    """fwav_build_tables (fused where the geometry allows) = the reference's domains, and the embeddings of the
+    stand-alone kernel bit for bit"""
+    g = golden(name)
+    tile, N, ds, ed = int(g["tile_size"]), int(g["range_size"]), int(g["domain_step"]), int(g["emb_dim"])
+    d_sig = ctx.upload(g["signal"])
+    n_d = len(g["domains"])
+    d_dom, d_emb, d_emb2 = ctx.alloc(n_d * N * 4), ctx.alloc(n_d * ed * 4), ctx.alloc(n_d * ed * 4)
+    ctx.build_tables(d_sig.ptr, len(g["signal"]), tile, N, ds, ed, d_dom.ptr, d_emb.ptr)
+    got = d_dom.to_host((n_d, N), np.float32)
+    assert np.array_equal(bits(got), bits(g["domains"]))
+    emb = d_emb.to_host((n_d, ed), np.float32)
+    assert np.abs(emb - g["embeddings"]).max() <= 2e-6
+    ctx.embed(d_dom.ptr, n_d, N, ed, d_emb2.ptr)
+    assert np.array_equal(bits(emb), bits(d_emb2.to_host((n_d, ed), np.float32)))
+
+
+@pytest.mark.parametrize("tile", [1024, 2048, 4096, 8192])
+def test_tables_in_one_pass_block_edges(ctx, tile):
+    """signal lengths around the block sizes of tables.cu (4 344 leaf starts, 512 domains per pass), a signal that
+    is not 16-byte aligned, and a length that leaves one domain"""
+    from fwav_b200 import _lib
+    N, ds = _lib.geometry(tile)
+    rng = np.random.default_rng(tile)
+    big = (rng.standard_normal(3 * 4344 * max(ds, 1) + tile + 700) * 10 ** rng.uniform(-3, 1, 3 * 4344 * max(ds, 1) + tile + 700)).astype(np.float32)
+    d_big = ctx.upload(big)
+    for n, off in [(tile, 0), (tile + ds, 0), (tile + 511 * ds, 0), (tile + 512 * ds, 4), (4344 + 127, 0), (4344 + 128, 0),
+                   (2 * 4344 + 135, 4), (len(big) - 8, 8), (len(big) - 1, 4), (len(big), 0)]:
+        if n < tile:
+            continue
+        sig = big[off // 4: off // 4 + n]
+        n_d = _lib.count_domains(n, tile, ds)
+        d_dom, d_emb, d_dom2, d_emb2 = (ctx.alloc(n_d * N * 4), ctx.alloc(n_d * 16 * 4), ctx.alloc(n_d * N * 4),
+                                        ctx.alloc(n_d * 16 * 4))
+        ctx.build_tables(d_big.ptr + off, n, tile, N, ds, 16, d_dom.ptr, d_emb.ptr)
+        got = d_dom.to_host((n_d, N), np.float32)
+        assert np.array_equal(bits(got), bits(O.build_domains(sig, tile, N, ds))), (n, off)
+        ctx.build_domains(d_big.ptr + off, n, tile, N, ds, d_dom2.ptr)
+        assert np.array_equal(bits(got), bits(d_dom2.to_host((n_d, N), np.float32))), (n, off)
+        ctx.embed(d_dom.ptr, n_d, N, 16, d_emb2.ptr)
+        assert np.array_equal(bits(d_emb.to_host((n_d, 16), np.float32)), bits(d_emb2.to_host((n_d, 16), np.float32))), (n, off)
+
+
 def test_embedding_generic_shapes(ctx):
     """emb_dim / range_size combinations outside the constant-bank kernels."""
     rng = np.random.default_rng(3)

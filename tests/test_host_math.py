@@ -1,11 +1,13 @@
 """The kernels' per-element math (np_math.cuh / fwav_math.cuh), compiled for the
 CPU, against numpy and the reference-generated golden vectors.  This is what
 makes the GPU results predictable before a GPU is touched."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
 from conftest import golden
-from host_harness import Harness
+from host_harness import Harness, _p
 
 H = Harness()
 ALL = ["tone128", "sine_t1024", "music_t4096", "gaps_t1024", "float_t1024",
@@ -36,6 +38,36 @@ def test_domains_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ALL)
+def test_domains_through_shared_chains_bit_exact(name):
+    """tables.cu's route (every chain of numpy's 128-sample leaf computed once, leaves from eight chains, rows from a
+    staged window of leaves), emulated block by block with the kernels' index arithmetic: the reference's bits."""
+    g = golden(name)
+    tile, N, ds = int(g["tile_size"]), int(g["range_size"]), int(g["domain_step"])
+    if tile // N != 256 or 128 % ds:
+        pytest.skip("run length is not 256: the generic kernel serves this geometry")
+    got, half = H.build_domains_chain(g["signal"], tile, N, ds)
+    assert not np.isnan(half).any(), "a leaf no block wrote"
+    assert np.array_equal(bits(got), bits(g["domains"]))
+
+
+@pytest.mark.parametrize("n, stride", [(128, 1), (129, 4), (4343 + 128, 1), (4344 + 128, 4), (4345 + 128, 1),
+                                       (3 * 4344 + 127, 1), (3 * 4344 + 131, 2), (20011, 3), (50000, 8), (70001, 4)])
+def test_chain_half_sums_equal_the_direct_leaf(n, stride):
+    """block edges of half_sums_chain_kernel (4344 leaf starts per block) and strides that are not powers of two"""
+    rng = np.random.default_rng(n + stride)
+    sig = (rng.standard_normal(n) * 10 ** rng.uniform(-3, 3, n)).astype(np.float32)
+    n_half = (n - 128) // stride + 1
+    half = np.full(n_half, np.nan, np.float32)
+    H.lib.hh_half_sums_chain(_p(sig), C.c_longlong(n), C.c_longlong(n_half), C.c_int(stride), _p(half))
+    assert not np.isnan(half).any(), "a leaf no block wrote"
+    # np_mean of 128 values = (0 + leaf) / 128 and the division is exact: equal means <=> equal leaves
+    edges = {min(n_half - 1, max(0, (b * 4344 + d) // stride)) for b in range(1, 4) for d in (-8, -1, 0, 1, 8)}
+    for u in sorted(set(range(0, n_half, max(1, n_half // 300))) | {0, n_half - 1} | edges):
+        got = np.float32((np.float32(0.0) + half[u]) / np.float32(128))
+        assert bits(got) == bits(H.np_mean(sig[u * stride: u * stride + 128])), u
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_embedding_close(name):
     g = golden(name)
     got = H.embed(g["domains"], int(g["emb_dim"]))
@@ -54,6 +86,31 @@ def test_affine_bit_exact_given_candidates(name):
         assert np.array_equal(bits(got[k]), bits(g[k])), k
     act = H.activity(g["ranges"], float(g["energy_thresh"]))
     assert np.array_equal(act == 0, (g["candidates"] < 0).all(axis=1))
+    # the kernel's form: both orientations in one go, tile statistics shared where mirroring cannot change them
+    pair = H.affine(g["ranges"], g["domains"], g["candidates"], pair=True)
+    assert np.array_equal(pair["idx"], g["idx"]) and np.array_equal(pair["sym"], g["sym"])
+    for k in ("s", "o", "err"):
+        assert np.array_equal(bits(pair[k]), bits(g[k])), k
+
+
+@pytest.mark.parametrize("N", [4, 8, 16, 32, 11])
+def test_affine_pair_equals_two_single_fits(N):
+    """fwm::affine_fit_pair against two fwm::affine_fit calls on adversarial rows: wide dynamic range, constant
+    tiles (den = 1e-12), signed zeros, rows equal to their own mirror"""
+    rng = np.random.default_rng(N)
+    n_d, n_r, K = 400, 300, 24
+    dom = (rng.standard_normal((n_d, N)) * 10.0 ** rng.integers(-6, 4, (n_d, 1))).astype(np.float32)
+    dom[::7] = dom[::7, :1]                       # constant tiles
+    dom[1::7] = (dom[1::7] + dom[1::7, ::-1]) / 2   # palindromes
+    dom[2::7] *= 0.0
+    dom[3::7] = -dom[2::7]
+    rngs = (rng.standard_normal((n_r, N)) * 10.0 ** rng.integers(-5, 3, (n_r, 1))).astype(np.float32)
+    rngs[::5] = dom[rng.integers(0, n_d, len(rngs[::5]))][:, ::-1]       # exact mirrored copies: err ties at 0
+    cand = rng.integers(-1, n_d, (n_r, K)).astype(np.int32)
+    a, b = H.affine(rngs, dom, cand), H.affine(rngs, dom, cand, pair=True)
+    assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["sym"], b["sym"])
+    for k in ("s", "o", "err"):
+        assert np.array_equal(bits(a[k]), bits(b[k])), k
 
 
 @pytest.mark.parametrize("name", ["tone128", "sine_t1024", "music_t4096", "gaps_t1024",
