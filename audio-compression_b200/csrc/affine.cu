@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "fwav_math.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -32,18 +34,47 @@ __device__ __forceinline__ bool better(float e1, int p1, float e2, int p2) {
     return e1 < e2 || (e1 == e2 && p1 < p2);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(256, NT == 16 ? 3 : 1)
+// PIPE = 0: every range loads its candidate indices, then the rows they name, then fits: two dependent memory
+// latencies per range in front of ~600 instructions of arithmetic.
+// PIPE = 1 (NT > 0, the first 32 candidates of a range): the warp's NEXT range is in flight while the current one
+// is fitted -- its candidate indices were loaded one range earlier, its rows are requested before the fits start
+// (NT more registers per lane) -- so the fits never wait for memory.
+template <int NT, int PIPE>
+__global__ void __launch_bounds__(256, NT == 16 ? (PIPE ? 2 : 3) : 1)
 affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
               const float *__restrict__ domains, long long n_d, const int32_t *__restrict__ cand, int K, float clipf,
               int32_t *__restrict__ o_idx, float *__restrict__ o_s, float *__restrict__ o_o,
               uint8_t *__restrict__ o_sym, float *__restrict__ o_err) {
+    constexpr int NR = NT > 0 ? NT : 1;
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // candidate index of this lane in the first chunk of range i (-1: none / padding / past the table)
+    auto load_raw = [&](long long i) -> int {
+        int raw = -1;
+        if (i < n_r && lane < K) raw = __ldg(cand + i * K + lane);
+        return raw >= n_d ? -1 : raw;                                 // caller-supplied table: never read past the domains
+    };
+    auto load_row = [&](int raw, float (&t)[NR]) {
+        if constexpr (NT > 0) {
+            const float4 *tp = reinterpret_cast<const float4 *>(domains + (long long)(raw < 0 ? 0 : raw) * NT);   // :772-773
+#pragma unroll
+            for (int k = 0; k < NT; k += 4) {
+                const float4 v = __ldg(tp + k / 4);
+                t[k] = v.x; t[k + 1] = v.y; t[k + 2] = v.z; t[k + 3] = v.w;
+            }
+        }
+    };
+    int raw_cur = -1, raw_next = -1;
+    float t_next[NR];
+    if constexpr (PIPE) {
+        raw_cur = load_raw(warp0);
+        raw_next = load_raw(warp0 + n_warps);
+        load_row(raw_cur, t_next);
+    }
     for (long long i = warp0; i < n_r; i += n_warps) {
         const float *rp = ranges + i * N;
-        float rreg[NT > 0 ? NT : 1];
+        float rreg[NR];
         if constexpr (NT > 0) {
 #pragma unroll
             for (int k = 0; k < NT; k += 4) {
@@ -51,12 +82,24 @@ affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
                 rreg[k] = v.x; rreg[k + 1] = v.y; rreg[k + 2] = v.z; rreg[k + 3] = v.w;
             }
         }
+        float t_cur[NR];
+        int raw0 = -1;
+        if constexpr (PIPE) {
+            // rotate: this range's rows arrived during the previous fits; request the next range's rows and the
+            // indices of the one after it
+            raw0 = raw_cur;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) t_cur[k] = t_next[k];
+            raw_cur = raw_next;
+            load_row(raw_cur, t_next);
+            raw_next = load_raw(i + 2 * n_warps);
+        }
         auto r = [&](int k) {
             if constexpr (NT > 0) return rreg[k];
             else return __ldg(rp + k);
         };
         const float r_mean = fwm::range_mean<NT>(r, N);
-        float rcreg[NT > 0 ? NT : 1];                                  // r - mean(r), once per range (:791)
+        float rcreg[NR];                                               // r - mean(r), once per range (:791)
         if constexpr (NT > 0) {
 #pragma unroll
             for (int k = 0; k < NT; ++k) rcreg[k] = npm::sub(rreg[k], r_mean);
@@ -70,20 +113,18 @@ affine_kernel(const float *__restrict__ ranges, long long n_r, int N,
         for (int c0 = 0; c0 < K; c0 += 32) {
             const int c = c0 + lane;
             if (c < K) {
-                int raw = __ldg(cand + i * K + c);
-                if (raw >= n_d) raw = -1;                             // caller-supplied table: never read past the domains
+                int raw;
+                if (PIPE && c0 == 0) {
+                    raw = raw0;
+                } else {
+                    raw = __ldg(cand + i * K + c);
+                    if (raw >= n_d) raw = -1;
+                    if constexpr (NT > 0) load_row(raw, t_cur);
+                }
                 const int d = raw < 0 ? 0 : raw;                      // :772-773
                 const float *tp = domains + (long long)d * N;
-                float treg[NT > 0 ? NT : 1];
-                if constexpr (NT > 0) {
-#pragma unroll
-                    for (int k = 0; k < NT; k += 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4 *>(tp + k));
-                        treg[k] = v.x; treg[k + 1] = v.y; treg[k + 2] = v.z; treg[k + 3] = v.w;
-                    }
-                }
                 auto plain = [&](int k) {
-                    if constexpr (NT > 0) return treg[k];
+                    if constexpr (NT > 0) return t_cur[k];
                     else return __ldg(tp + k);
                 };
                 // both orientations; for N = 8 / 16 the tile's mean, centred values and sum of squares are shared
@@ -129,14 +170,24 @@ int fwav_launch_affine(fwav_ctx *ctx, const float *d_ranges, int64_t n_r, int N,
     long long cap = (long long)ctx->num_sms * 8;
     const int grid = (int)(need < cap ? need : cap);
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_ranges) | reinterpret_cast<uintptr_t>(d_domains)) & 15) == 0;
-#define FWAV_AFFINE(NT)                                                                          \
-    affine_kernel<NT><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, (long long)n_d, d_cand, K, clipf, d_idx, \
-                                            d_s, d_o, d_sym, d_err)
+    // FWAV_AFFINE_PIPE=0 / 1: measurement knob for the software-pipelined form (default below)
+    const char *pipe_env = getenv("FWAV_AFFINE_PIPE");
+    const bool pipe = pipe_env ? atoi(pipe_env) != 0 : true;
+#define FWAV_AFFINE(NT)                                                                                        \
+    do {                                                                                                       \
+        if (pipe)                                                                                              \
+            affine_kernel<NT, 1><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, (long long)n_d, d_cand, K, clipf, d_idx, \
+                                                       d_s, d_o, d_sym, d_err);                                \
+        else                                                                                                   \
+            affine_kernel<NT, 0><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, (long long)n_d, d_cand, K, clipf, d_idx, \
+                                                       d_s, d_o, d_sym, d_err);                                \
+    } while (0)
     if (aligned && N == 4) FWAV_AFFINE(4);
     else if (aligned && N == 8) FWAV_AFFINE(8);
     else if (aligned && N == 16) FWAV_AFFINE(16);
     else if (aligned && N == 32) FWAV_AFFINE(32);
-    else FWAV_AFFINE(0);
+    else affine_kernel<0, 0><<<grid, 256, 0, st>>>(d_ranges, n_r, N, d_domains, (long long)n_d, d_cand, K, clipf, d_idx,
+                                                   d_s, d_o, d_sym, d_err);
 #undef FWAV_AFFINE
     FWAV_LAUNCH_CHECK(ctx);
     return FWAV_OK;

@@ -18,7 +18,7 @@
 namespace {
 
 template <int N, int HALF>
-__global__ void __launch_bounds__(128, N <= 16 ? 4 : 2)
+__global__ void __launch_bounds__(128, N <= 16 ? 6 : 5)
 embed_static_kernel(const float *__restrict__ rows, long long n_rows, float *__restrict__ emb,
                     const __grid_constant__ TablesP<N, HALF> T) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows;

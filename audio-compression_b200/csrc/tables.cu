@@ -96,7 +96,7 @@ half_sums_chain_kernel(const float *__restrict__ signal, long long n, long long 
 
 // run == 256, leaves at every DS-th sample (DS = domain_step divides 128), emb_dim 16
 template <int N, int DS>
-__global__ void __launch_bounds__(kTabThreads, N == 8 ? 4 : N <= 16 ? 5 : 2)
+__global__ void __launch_bounds__(kTabThreads, N <= 16 ? 7 : 6)
 tables_from_halves_kernel(const float *__restrict__ half, long long n_half, long long n_dom,
                           float *__restrict__ domains, float *__restrict__ emb,
                           const __grid_constant__ TablesP<N, 8> T) {

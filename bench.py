@@ -667,7 +667,7 @@ def run_extras(args, torch, dist, dev, local, ctx, t_start):
 def ncu_traffic(kernel):
     """DRAM bytes (read + write) per launch of the dominant kernel on config 2, from the committed
     `ncu --set full` captures (profiles/r02_ncu_full_collect_*.json; scripts/r02/gpu_n.sh, gpu_e.sh)."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_full_collect_hi_config2.json" if "collect_hi" in kernel
+    path = os.path.join(ROOT, "profiles", "r02_ncu_full_collect_hi_config2_v2.json" if "collect_hi" in kernel
                         else "r02_ncu_full_collect_f32acc_config2.json")
     if ("COLLECT" not in kernel and "collect_hi" not in kernel) or not os.path.exists(path):
         return None
@@ -678,10 +678,15 @@ def ncu_traffic(kernel):
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(rec[k]["value"]) * unit[rec[k]["unit"]]
         return {"bytes_per_launch": tot, "source": "ncu --set full, profiles/" + os.path.basename(path),
-                "note": "the packed domain table (hi parts, 63 MB) is re-streamed by every CTA and served from L2; DRAM "
-                        "sees 6-8 GB of reads (sector fills under the scattered 4-byte candidate-index stores: staging "
-                        "them as whole sectors was measured and cost more time than it saved, DESIGN 4.3) and 0.8 GB of "
-                        "writes per launch, ~2 % of peak"}
+                "algorithmic_bytes_per_launch": 63.5e6 + 4.0 * 256 * 496125,
+                "note": "4.7 GB of reads + 0.7 GB of writes per launch, 1.5 % of the HBM rate.  The reads are L2 misses of "
+                        "the TABLE stream, not sector fills under the 4-byte index stores (ncu: 341 M read-lookup misses "
+                        "against 34 M write-lookup misses; the writes bound the fills at 0.7 GB): every CTA re-streams the "
+                        "63 MB of hi tiles (244 GB per launch through L2, 97.9 % hits), the 3 848 CTAs make 26 laps, and a "
+                        "lap's tiles do not survive in L2 until the next one (63 MB per partition) -- 2 partitions x 26 laps "
+                        "x 63 MB = 3.3 GB is what this loop order costs; CTAs that share their position in the table "
+                        "(ScanArgs::front) brought it from 7.3 GB to 4.7, an evict_last hint on the tiles changed nothing "
+                        "(4.6 GB, same time: profiles/r02_collect_l2_traffic.txt)"}
     except Exception:
         return None
 

@@ -11,6 +11,7 @@
 #include "fwav_math.cuh"
 #include "embed_tables.h"
 #include "tables_geom.h"
+#include "embed_static.cuh"
 
 template <int NS, class R, class T>
 static fwm::Fit fit_dispatch(R r, float r_mean, T t, int N) {
@@ -50,6 +51,22 @@ static void affine_pair_rows(const float *ranges, long long n_r, int N, const fl
         o[i] = best_fit.o;
         sym[i] = best_pos >= K;
         err[i] = best_fit.err;
+    }
+}
+
+// the kernels' compile-time form of the two-head embedding (embed_static.cuh: half-length chains on the sums and
+// differences of mirrored samples)
+template <int N>
+static void embed_static_rows(const float *rows, long long n_rows, float *out) {
+    const FwavEmbedTables t = fwav_make_embed_tables(N, 8);
+    static TablesP<N, 8> P;
+    for (int i = 0; i < 8 * N; ++i) { P.tonal[i] = t.tonal[i]; P.transient[i] = t.transient[i]; }
+    for (int i = 0; i < N; ++i) P.w[i] = t.w[i];
+    for (long long r = 0; r < n_rows; ++r) {
+        float x[N], o[16];
+        for (int i = 0; i < N; ++i) x[i] = rows[r * N + i];
+        embed_row_static<N, 8>(x, P, o);
+        for (int i = 0; i < 16; ++i) out[r * 16 + i] = o[i];
     }
 }
 
@@ -127,6 +144,15 @@ void hh_embed(const float *rows, long long n_rows, int N, int emb_dim, float *ou
         float *o = out + r * emb_dim;
         for (int i = 0; i < emb_dim; ++i) o[i] = i < 2 * half ? tmp[i] : 0.0f;
     }
+}
+
+int hh_embed_static(const float *rows, long long n_rows, int N, float *out) {
+    if (N == 4) embed_static_rows<4>(rows, n_rows, out);
+    else if (N == 8) embed_static_rows<8>(rows, n_rows, out);
+    else if (N == 16) embed_static_rows<16>(rows, n_rows, out);
+    else if (N == 32) embed_static_rows<32>(rows, n_rows, out);
+    else return 1;
+    return 0;
 }
 
 void hh_embed_tonal(const float *rows, long long n_rows, int N, int k, float *out) {

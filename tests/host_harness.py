@@ -17,7 +17,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [SRC] + [os.path.join(INC, f) for f in ("np_math.cuh", "fwav_math.cuh", "embed_tables.h", "tables_geom.h")]
+    deps = [SRC] + [os.path.join(INC, f) for f in ("np_math.cuh", "fwav_math.cuh", "embed_tables.h", "tables_geom.h", "embed_static.cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -87,6 +87,14 @@ class Harness:
         rows = f32(rows)
         out = np.empty((rows.shape[0], emb_dim), np.float32)
         self.lib.hh_embed(_p(rows), C.c_longlong(rows.shape[0]), C.c_int(rows.shape[1]), C.c_int(emb_dim), _p(out))
+        return out
+
+    def embed_static(self, rows):
+        """embed_static.cuh (the kernels' form for range_size 4 / 8 / 16 / 32 at emb_dim 16); None for other sizes"""
+        rows = f32(rows)
+        out = np.empty((rows.shape[0], 16), np.float32)
+        if self.lib.hh_embed_static(_p(rows), C.c_longlong(rows.shape[0]), C.c_int(rows.shape[1]), _p(out)):
+            return None
         return out
 
     def activity(self, ranges, thr, fast=True):

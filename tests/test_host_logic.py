@@ -147,6 +147,60 @@ def test_wav_roundtrip(tmp_path, width):
         assert np.allclose(y, 1.0)
 
 
+def _plain_read(path):
+    """the reference's decode, step by step (fractal.py:81-112)"""
+    import wave
+    with wave.open(path, "rb") as w:
+        ch, width, raw = w.getnchannels(), w.getsampwidth(), w.readframes(w.getnframes())
+    if width == 1:
+        d = np.frombuffer(raw, np.uint8).astype(np.int16) - 128
+    elif width == 2:
+        d = np.frombuffer(raw, np.int16)
+    elif width == 3:
+        b = np.frombuffer(raw, np.uint8).reshape(-1, 3)
+        d = b[:, 0].astype(np.int32) | (b[:, 1].astype(np.int32) << 8) | (b[:, 2].astype(np.int32) << 16)
+        d = d - ((d & 0x800000) << 1)
+    else:
+        d = np.frombuffer(raw, np.float32)
+    if ch > 1:
+        d = d.reshape(-1, ch).mean(axis=1)
+    return d.astype(np.float32)
+
+
+@pytest.mark.parametrize("width, channels", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 1), (3, 2), (3, 4), (4, 1), (4, 2)])
+def test_wav_single_pass_forms_equal_the_plain_decode(tmp_path, width, channels):
+    """24-bit and stereo files (config 4's input) through the single-pass forms of wavio: the same float32 bits as
+    the reference's byte-by-byte decode, extremes and odd sums (x.5 means) included"""
+    import wave
+    import fractal
+    rng = np.random.default_rng(10 * width + channels)
+    n = 4001
+    if width == 4:
+        raw = rng.standard_normal((n, channels)).astype("<f4").tobytes()
+    elif width == 1:
+        raw = rng.integers(0, 256, (n, channels), dtype=np.uint8).tobytes()
+    else:
+        top = 2 ** (8 * width - 1)
+        v = rng.integers(-top, top, (n, channels), dtype=np.int64)
+        v[:4] = [[-top] * channels, [top - 1] * channels, [0] * channels, [-1] * channels]
+        raw = b"".join(int(x).to_bytes(width, "little", signed=True) for x in v.ravel())
+    p = str(tmp_path / "x.wav")
+    with wave.open(p, "wb") as f:
+        f.setnchannels(channels); f.setsampwidth(width); f.setframerate(48000); f.writeframes(raw)
+    got, rate, w = fractal.read_wav_mono(p)
+    want = _plain_read(p)
+    assert rate == 48000 and w == width and got.dtype == np.float32
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if channels == 1 and width == 3:
+        # write_wav's 24-bit packing against the reference's mask-and-shift form
+        fractal.write_wav(p, got * 1.5, 48000, 3)           # clips at both ends
+        d32 = (got * 1.5).clip(-2 ** 23, 2 ** 23 - 1).astype(np.int32)
+        ref = np.column_stack([(d32 & 0xFF).astype(np.uint8), ((d32 >> 8) & 0xFF).astype(np.uint8),
+                               ((d32 >> 16) & 0xFF).astype(np.uint8)]).flatten().tobytes()
+        with wave.open(p, "rb") as f:
+            assert f.readframes(f.getnframes()) == ref
+
+
 def test_api_surface_matches_reference():
     import inspect
     import fractal

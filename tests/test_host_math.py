@@ -74,6 +74,14 @@ def test_embedding_close(name):
     assert np.abs(got - g["embeddings"]).max() <= 2e-6
     # padding layout: [tonal | transient | zeros]
     assert np.array_equal(got == 0, g["embeddings"] == 0) or int(g["range_size"]) >= 9
+    # the kernels' compile-time form (half-length chains over mirrored sums / differences): the same gate, and
+    # float64 rounding noise apart from the full-length chains
+    if int(g["emb_dim"]) == 16:
+        st = H.embed_static(g["domains"])
+        if st is not None:
+            assert np.abs(st - g["embeddings"]).max() <= 2e-6
+            assert np.abs(st - got).max() <= 1.2e-7 and (st != got).mean() < 1e-2      # one float32 ulp, rarely
+            assert np.array_equal(st == 0, got == 0)
 
 
 @pytest.mark.parametrize("name", ALL)
