@@ -134,6 +134,18 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
                  : "l"(p));
     return v;
 }
+// 32 bytes per lane in one instruction (sm_100: LDG.E.256): random row gathers of 64-byte rows cost two requests per
+// row instead of four -- half the L1 wavefronts where every lane reads a different row (p must be 32-byte aligned)
+__device__ __forceinline__ void ldg_f8(const float *p, float *v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_stream_f8(float *p, const float *v) {      // p 32-byte aligned
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void st_stream_f4(float4 *p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                  "f"(v.y), "f"(v.z), "f"(v.w)

@@ -104,6 +104,7 @@ tables_from_halves_kernel(const float *__restrict__ half, long long n_half, long
     constexpr int W = kTabJ + (N * 256 - 128) / DS;  // half sums a pass of kTabJ domains touches
     __shared__ float hs[W];
     const int tid = threadIdx.x;
+    const bool wide = ((reinterpret_cast<uintptr_t>(domains) | reinterpret_cast<uintptr_t>(emb)) & 31) == 0;
     for (long long j0 = (long long)blockIdx.x * kTabJ; j0 < n_dom; j0 += (long long)gridDim.x * kTabJ) {
         for (int i = tid; i < W; i += kTabThreads) {
             const long long h = j0 + i;
@@ -118,18 +119,32 @@ tables_from_halves_kernel(const float *__restrict__ half, long long n_half, long
                 float x[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) x[k] = fwm::domain_from_halves(hs[jl + k * KS], hs[jl + k * KS + HS]);
-                float4 *drow = reinterpret_cast<float4 *>(domains + j * N);
+                // every lane stores its own row: 32-byte stores where the tables allow (half the requests)
+                if (N >= 8 && wide) {
 #pragma unroll
-                for (int k = 0; k < N / 4; ++k)
-                    st_stream_f4(drow + k, make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
-                float4 *erow = reinterpret_cast<float4 *>(emb + j * 16);
+                    for (int k = 0; k < N; k += 8) st_stream_f8(domains + j * N + k, x + k);
+                } else {
+                    float4 *drow = reinterpret_cast<float4 *>(domains + j * N);
+#pragma unroll
+                    for (int k = 0; k < N / 4; ++k)
+                        st_stream_f4(drow + k, make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]));
+                }
+                float *erow = emb + j * 16;
                 float out[8];
                 embed_tonal_static<N, 8>(x, T, out);
-                st_stream_f4(erow, make_float4(out[0], out[1], out[2], out[3]));
-                st_stream_f4(erow + 1, make_float4(out[4], out[5], out[6], out[7]));
+                if (wide) {
+                    st_stream_f8(erow, out);
+                } else {
+                    st_stream_f4(reinterpret_cast<float4 *>(erow), make_float4(out[0], out[1], out[2], out[3]));
+                    st_stream_f4(reinterpret_cast<float4 *>(erow) + 1, make_float4(out[4], out[5], out[6], out[7]));
+                }
                 embed_transient_static<N, 8>(x, T, out);
-                st_stream_f4(erow + 2, make_float4(out[0], out[1], out[2], out[3]));
-                st_stream_f4(erow + 3, make_float4(out[4], out[5], out[6], out[7]));
+                if (wide) {
+                    st_stream_f8(erow + 8, out);
+                } else {
+                    st_stream_f4(reinterpret_cast<float4 *>(erow) + 2, make_float4(out[0], out[1], out[2], out[3]));
+                    st_stream_f4(reinterpret_cast<float4 *>(erow) + 3, make_float4(out[4], out[5], out[6], out[7]));
+                }
             }
         }
         __syncthreads();

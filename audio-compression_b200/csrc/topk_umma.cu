@@ -1496,13 +1496,14 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x)
     return ((unsigned long long)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(kFinWarps * 32)
+__global__ void __launch_bounds__(kFinWarps * 32, 8)       // 64 registers: the row gathers need the warps (20 bytes spilled)
 finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long long n_q, long long n_d, int top_k,
                 const uint8_t *__restrict__ active, const float *theta, const int32_t *__restrict__ cbuf,
                 const int *__restrict__ ccount, int cap, int parts, int q_index0, const unsigned *__restrict__ norms,
                 int hi_only, int32_t *__restrict__ cand,
                 float *__restrict__ scores, int *__restrict__ fail_list, int *__restrict__ fail_count,
-                float *theta_retry /* may alias theta: a failed query's threshold for the second pass */, int key_cap) {
+                float *theta_retry /* may alias theta: a failed query's threshold for the second pass */, int key_cap,
+                float *theta_retry16 /* the same for a second pass that filters with fp16 accumulators (may be NULL) */) {
     extern __shared__ unsigned long long fin_keys[];       // [kFinWarps][key_cap]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * kFinWarps + warp;
@@ -1537,13 +1538,19 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         const float4 f = __ldg(reinterpret_cast<const float4 *>(Q + q * ED + k));
         qv[k] = f.x; qv[k + 1] = f.y; qv[k + 2] = f.z; qv[k + 3] = f.w;
     }
+    const bool wide_rows = (reinterpret_cast<uintptr_t>(E) & 31) == 0;     // the contract asks for 16-byte alignment only
     auto key_of = [&](int id) -> unsigned long long {
         if (id >= n_d) return 0ull;
         float ev[ED];
+        if (wide_rows) {                               // two 32-byte requests per row instead of four 16-byte ones
+            ldg_f8(E + (long long)id * ED, ev);
+            ldg_f8(E + (long long)id * ED + 8, ev + 8);
+        } else {
 #pragma unroll
-        for (int k = 0; k < ED; k += 4) {
-            const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
-            ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
+            for (int k = 0; k < ED; k += 4) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(E + (long long)id * ED + k));
+                ev[k] = f.x; ev[k + 1] = f.y; ev[k + 2] = f.z; ev[k + 3] = f.w;
+            }
         }
         return make_key(fwm::score_chain(qv, ev, ED), id);
     };
@@ -1553,7 +1560,23 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         unsigned long long k[kFinRegs];
 #pragma unroll
         for (int j = 0; j < kFinRegs; ++j) k[j] = 0ull;
-        {
+        if (parts == 4) {
+            // the main launch: four column groups.  Candidate number g = lane + 32 j of the query sits in the group
+            // its prefix sums name; every lane finds its ten indices first (independent loads), then scores them --
+            // no part-by-part walk with a divergent block per (part, j) pair
+            const int o1 = ccount[q * 4], o2 = o1 + ccount[q * 4 + 1], o3 = o2 + ccount[q * 4 + 2];
+            const int32_t *b = cbuf + q * 4 * (long long)cap;
+            int ids[kFinRegs];
+#pragma unroll
+            for (int j = 0; j < kFinRegs; ++j) {
+                const int g = lane + 32 * j;
+                const int part = (g >= o1) + (g >= o2) + (g >= o3);
+                const int first = part == 0 ? 0 : part == 1 ? o1 : part == 2 ? o2 : o3;
+                ids[j] = g < c ? __ldg(b + part * cap + (g - first)) : 0x7fffffff;     // past the end: key_of gives 0
+            }
+#pragma unroll
+            for (int j = 0; j < kFinRegs; ++j) k[j] = key_of(ids[j]);
+        } else {
             int off = 0;
             for (int p = 0; p < parts; ++p) {          // candidate number g of the query = part p, entry g - off
                 const int cn = ccount[q * parts + p];
@@ -1576,21 +1599,46 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
                 k[j + 1] = lo;
             }
         }
-        for (int r = 0; r < want; ++r) {
-            const unsigned long long best = warp_max_u64(k[0]);
-            if (best == 0ull) break;
-            if (k[0] == best) {                        // keys are unique: exactly one lane pops
+        // Selection, several keys per round: a head (largest key of a lane's sorted list) that beats every lane's
+        // SECOND key beats everything that is not a head, so all such heads are the next keys of the global order
+        // (the largest head always is one of them).  They are ranked among themselves (one shuffle per emitting
+        // lane), written in parallel and popped together: ~5 rounds for 32 keys instead of 32 rounds of warp maximum
+        // + pop (each 65 instructions, 60 % of this kernel).
+        while (n_sel < want) {
+            const unsigned long long h = k[0];
+            const unsigned long long s2 = warp_max_u64(k[1]);
+            const bool emit = h > s2;                              // (h == 0: an empty list never emits)
+            const unsigned em = __ballot_sync(kFull, emit);
+            if (em == 0) break;                                    // nothing left
+            const unsigned h_hi = (unsigned)(h >> 32), h_lo = (unsigned)h;
+            int rank = 0;
+            if (em & (em - 1)) {                                   // more than one: rank among the emitted heads
+                for (unsigned m = em; m; m &= m - 1) {
+                    const int src = __ffs(m) - 1;
+                    const unsigned o_hi = __shfl_sync(kFull, h_hi, src), o_lo = __shfl_sync(kFull, h_lo, src);
+                    rank += (o_hi > h_hi || (o_hi == h_hi && o_lo > h_lo)) ? 1 : 0;
+                }
+            }
+            const int pos = n_sel + rank;
+            if (emit && pos < want) {
+                cand[q * top_k + pos] = (int)(0xFFFFFFFFu - h_lo);
+                if (scores) scores[q * top_k + pos] = unorder_bits(h_hi);
+            }
+            if (n_sel == 0) {                                      // the best score of all (short queries use it)
+                const unsigned src = __ballot_sync(kFull, emit && rank == 0);
+                first = unorder_bits(__shfl_sync(kFull, h_hi, __ffs(src) - 1));
+            }
+            const int e = __popc(em);
+            if (n_sel + e >= want) {                               // the top_k-th key is among these
+                const unsigned src = __ballot_sync(kFull, emit && pos == want - 1);
+                last = unorder_bits(__shfl_sync(kFull, h_hi, __ffs(src) - 1));
+            }
+            if (emit) {
 #pragma unroll
                 for (int j = 0; j + 1 < kFinRegs; ++j) k[j] = k[j + 1];
                 k[kFinRegs - 1] = 0ull;
             }
-            if (lane == 0) {
-                cand[q * top_k + r] = (int)(0xFFFFFFFFu - (uint32_t)best);
-                if (scores) scores[q * top_k + r] = unorder_bits((uint32_t)(best >> 32));
-            }
-            last = unorder_bits((uint32_t)(best >> 32));
-            if (r == 0) first = last;
-            ++n_sel;
+            n_sel = n_sel + e < want ? n_sel + e : want;
         }
         ok = n_sel == want && last >= theta[q] + slack;
         for (int i = want + lane; i < top_k; i += 32) {      // table smaller than top_k: pad like the reference
@@ -1637,15 +1685,23 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
         // "boundary": enough candidates, but the last one sits within the slack of theta, so a better one may have
         // been filtered out.  Every domain that beats `last` scores at least last - slack_full on the tensor
         // cores with the full split: a second collect pass with this threshold finds them all and verifies.
-        if (theta_retry && !overflow && n_sel == want && want > 0) theta_retry[q] = fminf(theta[q], last - 2.0f * slack_full);
+        // A second pass on the fp16-accumulator filter needs the threshold below last - THAT filter's bound; a quarter
+        // of the bound on top keeps its proof (the top_k-th score can only rise) clear of its own threshold.
+        float t16 = theta[q];
+        if (theta_retry && !overflow && n_sel == want && want > 0) {
+            t16 = fminf(theta[q], last - 1.25f * score_slack(norms, 2));
+            theta_retry[q] = fminf(theta[q], last - 2.0f * slack_full);
+        }
         // "short": fewer than top_k domains reach theta at all (the tail of the sampled estimate: a handful of queries
         // per half million).  The same threshold would fail the same way, and the exact list kernel costs ~0.8 ms
         // however few queries it gets: the second pass has many times the buffer room, so it looks twice as far below
         // the best score found (any threshold is valid: the proof is checked against whatever was used).
         else if (theta_retry && !overflow && n_sel < want) {
             const float t = theta[q];
-            theta_retry[q] = t - fmaxf(n_sel > 0 ? first - t : 0.0f, 0.02f);
+            t16 = t - fmaxf(n_sel > 0 ? first - t : 0.0f, 0.02f);
+            theta_retry[q] = t16;
         }
+        if (theta_retry16) theta_retry16[q] = t16;
     }
 }
 
@@ -2169,6 +2225,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
             }
         }
 #endif
+        // A batch that took the fp16-accumulator route gives its failed queries their second chance on the same
+        // kernel (2.3 x cheaper per stage than the full split): a boundary case only needs its threshold below
+        // (K-th score - the filter's bound), whatever the filter; the table split gives it the room.
+        const bool retry16_ok = acc16 && !compact && single && !(mode_env && !strcmp(mode_env, "noretry")) &&
+                                !(getenv("FWAV_UMMA_RETRY16") && atoi(getenv("FWAV_UMMA_RETRY16")) == 0);
         for (int part = 0; part < (tail_groups ? 2 : 1); ++part) {
             const ScanArgs &ax = part ? at : a;
             const long long qoff = part ? main_q : 0;
@@ -2182,7 +2243,7 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 ax.Q, d_emb, ax.n_q, n_d, top_k, ax.active, ax.theta, ax.cbuf, ax.ccount, ax.cap, parts, (int)qoff,
                 d_norms, acc16 ? 2 : hi_only ? 1 : 0, d_cand + (q0 + qoff) * top_k,
                 d_scores ? d_scores + (q0 + qoff) * top_k : nullptr, d_fail, d_fail_count,
-                d_theta + q0 + qoff, key_cap);
+                d_theta + q0 + qoff, key_cap, d_theta_hi + q0 + qoff);     // (theta_hi has served its purpose: count_flat_kernel)
             FWAV_LAUNCH_CHECK(ctx);
         }
         if ((rc = mark(ctx, slot, 4, st))) return rc;
@@ -2232,6 +2293,11 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 // scores, 2 % of config 4's queries -- only need their threshold lowered, not more room; without the
                 // second pass they would all go to the FFMA kernel: 477 ms per million queries of the config-4 shape)
                 const bool retry = single && !(mode_env && !strcmp(mode_env, "noretry"));
+                // the fp16 second chance lowers a boundary case's threshold by 1.25 x ITS bound (5e-3 for two unit heads),
+                // which on crowded scores multiplies the candidates: only where the table split gives a query at least
+                // twice the room of the first pass (few failures); many failures keep the full split and its tight margin
+                // (a 15-minute signal: 5-8 k of 48-60 k retried queries per batch overflowed with rs = 1)
+                const bool retry16 = retry16_ok && rs >= 4;
                 int n_fail2 = n_fail;
                 const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
                 if (retry) {
@@ -2239,23 +2305,28 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     int32_t *d_rbuf = nullptr;
                     const size_t nb = (size_t)n_fail * rs * 4 * rcap * sizeof(int32_t), nc = (size_t)n_fail * rs * 4 * sizeof(int);
                     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_rbuf))) return rc;
-                    gather_f32_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>(d_theta + q0, d_fail, n_fail, d_ftheta);
+                    gather_f32_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>((retry16 ? d_theta_hi : d_theta) + q0, d_fail, n_fail, d_ftheta);
                     FWAV_LAUNCH_CHECK(ctx);
                     FWAV_CUDA(ctx, cudaMemsetAsync(d_fail2 + n_fail, 0, 4 * sizeof(int), st));
                     ScanArgs ar = a;
                     ar.q_tiles = d_fqt; ar.Q = d_fq; ar.n_q = n_fail; ar.active = nullptr; ar.theta = d_ftheta;
                     ar.n_split = (int)rs; ar.cbuf = d_rbuf; ar.cap = rcap;
                     ar.ccount = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(d_rbuf) + nb);
-                    rc = compact ? launch_scan<MODE_COLLECT, false, 1, true>(ctx, ar, fg, rs, st)
+                    if (retry16) {
+                        if (ar.front) FWAV_CUDA(ctx, cudaMemsetAsync(d_front, 0, 16 * sizeof(int), st));      // rs <= 16
+                        rc = launch_collect_hi(ctx, ar, fg, rs, st);
+                    } else {
+                        rc = compact ? launch_scan<MODE_COLLECT, false, 1, true>(ctx, ar, fg, rs, st)
                                      : launch_scan<MODE_COLLECT, false, 1>(ctx, ar, fg, rs, st);
+                    }
                     if (rc) return rc;
                     const int parts = 4 * (int)rs;
                     const size_t fin_smem = (size_t)kFinWarps * parts * rcap * sizeof(unsigned long long);
                     if (fin_smem > 48 * 1024)
                         FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
                     finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
-                        d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, d_norms, 0,
-                        d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, parts * rcap);
+                        d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, d_norms,
+                        retry16 ? 2 : 0, d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, parts * rcap, nullptr);
                     FWAV_LAUNCH_CHECK(ctx);
                     int h_fail2[4] = {0, 0, 0, 0};
                     FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail2, d_fail2 + n_fail, sizeof h_fail2, cudaMemcpyDeviceToHost, st));
@@ -2263,8 +2334,8 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     n_fail2 = h_fail2[0];
                     d_list2 = d_fail2;
                     if (getenv("FWAV_UMMA_VERBOSE"))
-                        fprintf(stderr, "[fwav] search batch at %lld: second chance (full split, table split %lld ways): %d of %d fail again (overflow %d, short %d, boundary %d)\n",
-                                q0, rs, n_fail2, n_fail, h_fail2[1], h_fail2[2], h_fail2[3]);
+                        fprintf(stderr, "[fwav] search batch at %lld: second chance (%s, table split %lld ways): %d of %d fail again (overflow %d, short %d, boundary %d)\n",
+                                q0, retry16 ? "hi*hi, fp16 accumulators" : "full split", rs, n_fail2, n_fail, h_fail2[1], h_fail2[2], h_fail2[3]);
                 }
                 ctx->umma_ffma_queries += n_fail2;     // (the list kernel's, for top_k <= 32)
                 if (n_fail2 > 0) {

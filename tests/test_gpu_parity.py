@@ -496,6 +496,43 @@ def test_large_search_properties(ctx):
         assert np.array_equal(results["umma"], got)
 
 
+def test_tables_aligned_to_16_bytes_only(ctx):
+    """The contract asks for 16-byte aligned tables; finalize_kernel, the affine kernel and the table pass use 32-byte
+    requests where the tables allow and 16-byte ones otherwise.  Tables placed 16 bytes into their buffers must give
+    the results of 32-byte aligned ones."""
+    import ctypes as C
+    from fwav_b200 import _lib, synth
+    sig = synth.music_like(seconds=8.0, rate=44100, seed=11)
+    tile, N, ds, K, ED = 4096, 16, 4, 32, 16
+    n_d = _lib.count_domains(len(sig), tile, ds)
+    n_q = 3000
+    assert n_d >= 1 << 16
+    d_sig = ctx.upload(sig)
+    frames = np.ascontiguousarray(sig[: n_q * N].reshape(n_q, N))
+    d_rng = ctx.upload(frames)
+    out = {}
+    for off in (0, 16):
+        d_dom, d_emb = ctx.alloc(n_d * N * 4 + 32), ctx.alloc(n_d * ED * 4 + 32)
+        dom, emb = d_dom.ptr + off, d_emb.ptr + off
+        ctx.build_tables(d_sig.ptr, len(sig), tile, N, ds, ED, dom, emb)
+        d_cand, d_sc = ctx.alloc(n_q * K * 4), ctx.alloc(n_q * K * 4)
+        set_impl(ctx, "umma")
+        try:
+            ctx.topk(emb, n_q, emb, n_d, ED, K, None, d_cand.ptr, d_sc.ptr)
+        finally:
+            set_impl(ctx, "auto")
+        d_idx, d_s, d_o, d_e, d_y = (ctx.alloc(n_q * 4) for _ in range(5))
+        ctx.affine_match(d_rng.ptr, n_q, N, dom, n_d, d_cand.ptr, K, 16.0, d_idx.ptr, d_s.ptr, d_o.ptr, d_y.ptr, d_e.ptr)
+        h_dom, h_emb = np.empty((n_d, N), np.float32), np.empty((n_d, ED), np.float32)
+        ctx._check(ctx.lib.fwav_memcpy_d2h(ctx.h, h_dom.ctypes.data_as(C.c_void_p), dom, h_dom.nbytes, None))
+        ctx._check(ctx.lib.fwav_memcpy_d2h(ctx.h, h_emb.ctypes.data_as(C.c_void_p), emb, h_emb.nbytes, None))
+        out[off] = (h_dom, h_emb, d_cand.to_host((n_q, K), np.int32), d_sc.to_host((n_q, K), np.float32),
+                    d_idx.to_host((n_q,), np.int32), d_s.to_host((n_q,), np.float32), d_o.to_host((n_q,), np.float32),
+                    d_e.to_host((n_q,), np.float32), d_y.to_host((n_q,), np.uint8)[:n_q])
+    for a, b in zip(out[0], out[16]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_search_paths_agree(ctx, monkeypatch):
     """The tensor-core search has three routes (sampled-threshold fast path, exact list kernel, list
     kernel split over the table for few queries).  On one table, with a pruning mask, every route has
