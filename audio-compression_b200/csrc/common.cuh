@@ -46,7 +46,7 @@ struct fwav_ctx {
     size_t ws_bytes[32] = {0};
     void *pinned = nullptr;               // staging ring of the host-buffer entry points (api.cu)
     size_t pinned_bytes = 0;
-    cudaEvent_t ring_ev[4] = {};
+    cudaEvent_t ring_ev[16] = {};
 };
 
 // scratch slots

@@ -2293,15 +2293,16 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 // scores, 2 % of config 4's queries -- only need their threshold lowered, not more room; without the
                 // second pass they would all go to the FFMA kernel: 477 ms per million queries of the config-4 shape)
                 const bool retry = single && !(mode_env && !strcmp(mode_env, "noretry"));
-                // the fp16 second chance lowers a boundary case's threshold by 1.25 x ITS bound (5e-3 for two unit heads),
-                // which on crowded scores multiplies the candidates: only where the table split gives a query at least
-                // twice the room of the first pass (few failures); many failures keep the full split and its tight margin
-                // (a 15-minute signal: 5-8 k of 48-60 k retried queries per batch overflowed with rs = 1)
-                const bool retry16 = retry16_ok && rs >= 4;
+                // The fp16 second chance lowers a boundary case's threshold by 1.25 x ITS bound (5e-3 for two unit heads),
+                // which on crowded scores multiplies the candidates (a 15-minute signal with the first pass's 256 entries
+                // per column group: 11-20 % of the retried queries overflowed): it gets at least 4 096 entries per query,
+                // from the table split where there are few failures, from larger buffers where there are many.
+                const bool retry16 = retry16_ok;
                 int n_fail2 = n_fail;
                 const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
                 if (retry) {
-                    const int rcap = rs > 8 ? collect_cap / 4 : rs >= 2 ? collect_cap / 2 : collect_cap;
+                    int rcap = rs > 8 ? collect_cap / 4 : rs >= 2 ? collect_cap / 2 : collect_cap;
+                    if (retry16 && rs < 4) rcap = ((int)(4096 / (4 * rs)) + 1) & ~1;        // 1 024 / 512 / 342 per column group
                     int32_t *d_rbuf = nullptr;
                     const size_t nb = (size_t)n_fail * rs * 4 * rcap * sizeof(int32_t), nc = (size_t)n_fail * rs * 4 * sizeof(int);
                     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_rbuf))) return rc;
