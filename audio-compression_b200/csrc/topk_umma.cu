@@ -2303,6 +2303,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 if (retry) {
                     int rcap = rs > 8 ? collect_cap / 4 : rs >= 2 ? collect_cap / 2 : collect_cap;
                     if (retry16 && rs < 4) rcap = ((int)(4096 / (4 * rs)) + 1) & ~1;        // 1 024 / 512 / 342 per column group
+                    // (a part of a finely split table still sees a whole cluster of neighbouring domains: with 64 entries
+                    // per part the retried queries of an eighth of config 2 -- 16 CTAs per 128 of them -- overflowed single
+                    // parts and paid for the list kernel, 0.8-2 ms on the slowest of 8 ranks)
+                    if (retry16 && rcap < 128) rcap = 128;
                     int32_t *d_rbuf = nullptr;
                     const size_t nb = (size_t)n_fail * rs * 4 * rcap * sizeof(int32_t), nc = (size_t)n_fail * rs * 4 * sizeof(int);
                     if ((rc = fwav_ws_reserve(ctx, WS_UMMA_TAIL, nb + nc, (void **)&d_rbuf))) return rc;
@@ -2322,12 +2326,13 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                     }
                     if (rc) return rc;
                     const int parts = 4 * (int)rs;
-                    const size_t fin_smem = (size_t)kFinWarps * parts * rcap * sizeof(unsigned long long);
+                    const int key_cap2 = parts * rcap < 4096 ? parts * rcap : 4096;      // keys per query the verification holds (more: an overflow)
+                    const size_t fin_smem = (size_t)kFinWarps * key_cap2 * sizeof(unsigned long long);
                     if (fin_smem > 48 * 1024)
                         FWAV_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
                     finalize_kernel<<<(unsigned)((n_fail + kFinWarps - 1) / kFinWarps), kFinWarps * 32, fin_smem, st>>>(
                         d_fq, d_emb, n_fail, n_d, top_k, nullptr, d_ftheta, ar.cbuf, ar.ccount, rcap, parts, 0, d_norms,
-                        retry16 ? 2 : 0, d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, parts * rcap, nullptr);
+                        retry16 ? 2 : 0, d_fc, d_fs, d_fail2, d_fail2 + n_fail, nullptr, key_cap2, nullptr);
                     FWAV_LAUNCH_CHECK(ctx);
                     int h_fail2[4] = {0, 0, 0, 0};
                     FWAV_CUDA(ctx, cudaMemcpyAsync(h_fail2, d_fail2 + n_fail, sizeof h_fail2, cudaMemcpyDeviceToHost, st));

@@ -334,7 +334,16 @@ def run_ours(args):
             per_stage[i] += ev[i].elapsed_time(ev[i + 1])
     ms_per_step = total_ms / args.steps
     per_stage /= args.steps
+    per_rank = None
     if world > 1:
+        # every rank's own view (its search stage, the collect pass of its last step, the route it took, its queries):
+        # the step is the slowest rank's, and the others wait for it in the gather
+        mine = torch.tensor([float(per_stage[stage_names.index("topk")]), float((search_ms or {}).get("collect", 0.0)),
+                             float(route), float(cnt), float((search_ms or {}).get("lists", 0.0))], dtype=torch.float64, device=dev)
+        allr = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [{"search_ms": round(r[0], 3), "collect_ms": round(r[1], 3), "route": int(r[2]), "ranges": int(r[3]),
+                     "second_chance_ms": round(r[4], 3)} for r in allr.cpu().tolist()]
         t = torch.tensor([ms_per_step] + per_stage.tolist(), dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step, per_stage = float(t[0]), t[1:].cpu().numpy()
@@ -409,6 +418,7 @@ def run_ours(args):
         t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": n_r / float(t[0]), "unit": "ranges/s", "ms_per_step": float(t[0]) * 1e3,
+               "ms_each_rank0": [round(x * 1e3, 3) for x in ts],
                "h2d_bytes_per_step": int(4 * n), "d2h_bytes_per_step": int(20 * cap * world),
                "call": "sharded device pipeline incl. H2D of the raw signal on every rank, the device pre-step and D2H of "
                        "the gathered matches on rank 0"}
@@ -510,7 +520,8 @@ def run_ours(args):
                                     "float32 finalize with per-query verification, second tensor-core pass then exact "
                                     "list/FFMA kernel for queries that fail it" if tensor else "FP32 FFMA"),
                     "parallelism": f"ranges sharded x{world}" + ((", tables " + ("NCCL-broadcast from rank 0" if args.bcast else "rebuilt on every rank") + ", matches all-gathered in one packed block") if world > 1 else ""),
-                    "l2": "flushed between timed steps (256 MiB device write outside the event pairs)"},
+                    "l2": "flushed between timed steps (256 MiB device write outside the event pairs)",
+                    "per_rank": per_rank},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "kernels": kern, "decode": decode,
         "peaks": peaks, "extra": extra,
