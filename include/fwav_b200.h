@@ -237,7 +237,7 @@ int fwav_prepare_ranges(fwav_ctx *ctx, const float *d_signal, int64_t n_samples,
 /* compress_audio from the RAW signal (what fractal.compress_audio calls): fwav_prepare_ranges on the device, then
  * the pipeline of fwav_compress_host; n_ranges = ceil(n_samples / range_size).  h_ranges (may be NULL) receives
  * the framed ranges.  *silent is set to 1, and no output is written, when the reference returns its empty result
- * for a silent input (:1083-1093).  Pageable buffers are staged through a context-owned page-locked ring in 8 MB
+ * for a silent input (:1083-1093).  Pageable buffers are staged through a context-owned page-locked ring in 2 MB
  * chunks (upload on the calling thread, download of the domain table on a helper thread beside the search);
  * page-locked buffers (fwav_host_alloc) are the end points of the asynchronous copies themselves. */
 int fwav_compress_signal_host(fwav_ctx *ctx, const float *h_signal, int64_t n_samples,

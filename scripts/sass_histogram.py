@@ -21,8 +21,8 @@ with open(out, "w") as f:
         tot = sum(c.values())
         sel = {p: sum(v for o, v in c.items() if o.startswith(p)) for p in KEY}
         f.write("%-110s total %6d  " % (k[:110], tot) + " ".join("%s=%d" % (p, v) for p, v in sel.items() if v) + "\n")
-    f.write("\n# full histogram of the dominant kernel\n")
+    f.write("\n# full histograms: the dominant kernel (collect pass, fp16 accumulators), its float32-accumulator form, the verification pass\n")
     for k, c in hist.items():
-        if "scan_kernel<2, true, 1" in k:
+        if "collect_hi_kernel<false>" in k or "scan_kernel<2, true, 1" in k or k.startswith("finalize_kernel"):
             f.write(k + "\n" + "\n".join("  %-28s %d" % (o, v) for o, v in c.most_common()) + "\n")
 print("kernels:", len(hist))
