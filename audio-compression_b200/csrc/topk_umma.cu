@@ -2297,7 +2297,10 @@ int fwav_launch_topk_umma(fwav_ctx *ctx, const float *d_q, int64_t n_q, const fl
                 // which on crowded scores multiplies the candidates (a 15-minute signal with the first pass's 256 entries
                 // per column group: 11-20 % of the retried queries overflowed): it gets at least 4 096 entries per query,
                 // from the table split where there are few failures, from larger buffers where there are many.
-                const bool retry16 = retry16_ok;
+                // (Degenerate data -- pure tones, digital silence: most of a batch tied within the bound -- would ask
+                // for gigabytes of such buffers: past 2 GB the full split and its tight margin take over, as before.)
+                const bool retry16 = retry16_ok &&
+                                     (rs >= 4 || (size_t)n_fail * 4096 * sizeof(int32_t) <= ((size_t)2 << 30));
                 int n_fail2 = n_fail;
                 const int *d_list2 = nullptr;      // FFMA input rows: indices into the gathered table (nullptr: all of it)
                 if (retry) {
