@@ -230,3 +230,61 @@ def test_experimental_collect_protocol_simulation():
     for n_visit in (2, 6, 34, 70):
         for seed in range(4):
             sim.run(n_visit, seed)
+
+
+def _select_rounds(lists, want):
+    """finalize_kernel's selection, lane by lane (topk_umma.cu): every round emits the heads that beat the largest
+    SECOND key of any lane, ranked among themselves; returns (selected keys in output order, first, last, rounds)"""
+    lists = [sorted(l, reverse=True) + [0, 0] for l in lists]          # 0 = empty slot
+    out, n_sel, first, last, rounds = [None] * want, 0, None, None, 0
+    while n_sel < want:
+        heads = [l[0] for l in lists]
+        s2 = max(l[1] for l in lists)
+        emit = [h > s2 for h in heads]
+        if not any(emit):
+            break
+        rounds += 1
+        e = sum(emit)
+        rank = [sum(1 for m in range(32) if emit[m] and heads[m] > heads[l]) for l in range(32)]
+        for l in range(32):
+            if emit[l] and n_sel + rank[l] < want:
+                out[n_sel + rank[l]] = heads[l]
+        if n_sel == 0:
+            first = next(heads[l] for l in range(32) if emit[l] and rank[l] == 0)
+        if n_sel + e >= want:
+            last = next(heads[l] for l in range(32) if emit[l] and n_sel + rank[l] == want - 1)
+        for l in range(32):
+            if emit[l]:
+                lists[l].pop(0)
+        n_sel = min(n_sel + e, want)
+    return out[:n_sel] if n_sel < want else out, first, last, rounds, n_sel
+
+
+@pytest.mark.parametrize("want", [32, 64])
+def test_selection_by_heads_above_every_second_key_is_a_sort(want):
+    """The verification pass selects several keys per round: any distribution of unique keys over the
+    32 lanes must come out as the `want` largest in descending order, with the first and the want-th reported --
+    random spreads, everything in one lane, fewer keys than wanted, exactly `want` keys."""
+    rng = np.random.default_rng(want)
+    cases = []
+    for n in (5, want - 1, want, want + 1, 200, 256, 320):
+        keys = (rng.permutation(10 ** 6)[:n] + 1).tolist()
+        cases.append([keys[l::32] for l in range(32)])                               # the kernel's interleaving
+        skew = [[] for _ in range(32)]
+        for i, k in enumerate(sorted(keys, reverse=True)):                           # the largest keys crowd a few lanes
+            skew[(i // 10) % 32].append(k)
+        cases.append(skew)
+    one = [[] for _ in range(32)]
+    one[7] = list(range(1, 11))
+    cases.append(one)
+    total_rounds = []
+    for lists in cases:
+        assert all(len(l) <= 10 for l in lists)                                      # kFinRegs
+        keys = sorted((k for l in lists for k in l), reverse=True)
+        out, first, last, rounds, n_sel = _select_rounds(lists, want)
+        assert n_sel == min(want, len(keys)) and out == keys[:n_sel]
+        assert first == keys[0]
+        if len(keys) >= want:
+            assert last == keys[want - 1]
+        total_rounds.append(rounds)
+    assert max(total_rounds) <= want                                                 # never worse than one key per round
