@@ -9,6 +9,7 @@ follows; n_domains*range_size f32; n_ranges 17-byte records
 """
 from __future__ import annotations
 
+import gc
 import hashlib
 import struct
 
@@ -71,8 +72,16 @@ class MatchArrays:
     def tolist(self):
         """The reference's representation: Python ints/floats widened from f32
         (fractal.py:836-845)."""
-        return list(zip(self.idx.tolist(), self.s.tolist(), self.o.tolist(),
-                        self.sym.tolist(), self.err.tolist()))
+        # half a million tuples are 2.5 M new objects: with the cyclic collector running the build costs 175-440 ms
+        # (it rescans the growing list again and again), paused 140 ms; nothing built here can form a cycle
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return list(zip(self.idx.tolist(), self.s.tolist(), self.o.tolist(),
+                            self.sym.tolist(), self.err.tolist()))
+        finally:
+            if was_enabled:
+                gc.enable()
 
     def records(self):
         rec = np.empty(len(self), dtype=RECORD)
