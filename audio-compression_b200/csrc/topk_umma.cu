@@ -1556,7 +1556,7 @@ finalize_kernel(const float *__restrict__ Q, const float *__restrict__ E, long l
     };
     if (ok && c <= 32 * kFinRegs) {
         // the usual case: at most kFinRegs candidates per lane, kept in registers.  Every lane sorts its own keys
-        // (descending); a round is then a warp maximum over the lanes' heads and one pop.
+        // (descending); the selection below then works on the lanes' heads.
         unsigned long long k[kFinRegs];
 #pragma unroll
         for (int j = 0; j < kFinRegs; ++j) k[j] = 0ull;
